@@ -1,0 +1,66 @@
+/*
+ * monodetr_b200.h -- C ABI of libmonodetr_b200.so (B200 / sm_100a).
+ *
+ * Plain pointers and sizes only; every pointer is a DEVICE pointer unless its comment says HOST.
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Every entry point is
+ * asynchronous on `stream`, never synchronises, never creates streams, and returns 0 on success,
+ * a positive cudaError_t value if the launch failed, or a negative MDB_E* code for bad arguments.
+ * (The reference only printf()s launch errors -- ms_deform_im2col_cuda.cuh:948-952,1321-1325 -- the
+ * host side of this library turns a non-zero return into a Python RuntimeError instead.)
+ *
+ * Reference interface each group replaces (paths relative to /root/reference):
+ *   mdb_msda_*          lib/models/monodetr/ops/src/vision.cpp:13-16  (pybind ms_deform_attn_forward/backward)
+ *                       lib/models/monodetr/ops/src/ms_deform_attn.h:20-61 (dispatch)
+ *                       lib/models/monodetr/ops/src/cuda/ms_deform_attn_cuda.cu:20-80, 83-153 (host launchers)
+ *                       lib/models/monodetr/ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299, 301-403 (kernels)
+ */
+#ifndef MONODETR_B200_H_
+#define MONODETR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDB_EINVAL (-1)      /* bad size / null pointer / misaligned pointer */
+#define MDB_EUNSUPPORTED (-2) /* shape outside what the kernels implement */
+
+/* Library/ABI version (bumped when a signature changes). */
+int mdb_abi_version(void);
+/* Human-readable name of the last error code returned on this thread ("ok" if 0). HOST string. */
+const char* mdb_error_string(int code);
+
+/* ---- Multi-scale deformable attention (MSDeformAttn core) -----------------------------------
+ * value          (B, S, M, D)          contiguous
+ * spatial_shapes (L, 2) int64 (H_l, W_l), device        [ms_deform_attn_cuda.cu:28-38 asserts the same]
+ * level_start    (L,)   int64, device
+ * sampling_loc   (B, Lq, M, L, P, 2)   (x, y) normalised to [0,1]
+ * attn_weight    (B, Lq, M, L, P)
+ * out            (B, Lq, M*D)          fully written by the call
+ * Any B is accepted (the reference's im2col_step chunking, ms_deform_attn_cuda.cu:50-52, is not needed).
+ */
+int mdb_msda_forward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                         const float* sampling_loc, const float* attn_weight,
+                         int B, int S, int M, int D, int L, int Lq, int P,
+                         float* out, void* stream);
+int mdb_msda_forward_f64(const double* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                         const double* sampling_loc, const double* attn_weight,
+                         int B, int S, int M, int D, int L, int Lq, int P,
+                         double* out, void* stream);
+
+/* Backward.  grad_value (B,S,M,D) is zero-filled by the call and then accumulated with atomics
+ * (ms_deform_attn_cuda.cu:121-123 + cuh:125-152); grad_loc / grad_attn are fully written. */
+int mdb_msda_backward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                          const float* sampling_loc, const float* attn_weight, const float* grad_out,
+                          int B, int S, int M, int D, int L, int Lq, int P,
+                          float* grad_value, float* grad_loc, float* grad_attn, void* stream);
+int mdb_msda_backward_f64(const double* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                          const double* sampling_loc, const double* attn_weight, const double* grad_out,
+                          int B, int S, int M, int D, int L, int Lq, int P,
+                          double* grad_value, double* grad_loc, double* grad_attn, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MONODETR_B200_H_ */

@@ -1,0 +1,59 @@
+"""ctypes loader for libmonodetr_b200.so (the C-ABI product library).
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmonodetr_b200.so")
+_lib = None
+
+c_int, c_void_p, c_float = ctypes.c_int, ctypes.c_void_p, ctypes.c_float
+
+# name -> argtypes (restype is always int unless listed in _RESTYPES)
+_PTR = c_void_p
+SIGNATURES = {
+    "mdb_abi_version": [],
+    "mdb_error_string": [c_int],
+    "mdb_msda_forward_f32": [_PTR] * 5 + [c_int] * 7 + [_PTR, _PTR],
+    "mdb_msda_forward_f64": [_PTR] * 5 + [c_int] * 7 + [_PTR, _PTR],
+    "mdb_msda_backward_f32": [_PTR] * 6 + [c_int] * 7 + [_PTR] * 4,
+    "mdb_msda_backward_f64": [_PTR] * 6 + [c_int] * 7 + [_PTR] * 4,
+}
+_RESTYPES = {"mdb_error_string": ctypes.c_char_p}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m monodetr_b200.build` "
+                "(there is no CPU / PyTorch fallback for the hot path)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the symbol is missing
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, c_int)
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().mdb_error_string(rc)
+        raise RuntimeError(f"monodetr_b200 {what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+# number of kernels of THIS library launched so far in this process (bench.py reports the per-step delta)
+_launches = 0
+
+
+def count(n: int = 1):
+    global _launches
+    _launches += n
+
+
+def launch_count() -> int:
+    return _launches

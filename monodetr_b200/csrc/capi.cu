@@ -1,0 +1,18 @@
+// capi.cu -- ABI version and error strings of libmonodetr_b200.so (see include/monodetr_b200.h).
+#include <cuda_runtime.h>
+
+#include "../../include/monodetr_b200.h"
+
+extern "C" {
+
+int mdb_abi_version(void) { return 1; }
+
+const char* mdb_error_string(int code) {
+    if (code == 0) return "ok";
+    if (code == MDB_EINVAL) return "monodetr_b200: invalid argument (size, null or misaligned pointer)";
+    if (code == MDB_EUNSUPPORTED) return "monodetr_b200: shape not supported by the sm_100a kernels";
+    if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+    return "monodetr_b200: unknown error";
+}
+
+}  // extern "C"

@@ -1,0 +1,498 @@
+// msda.cu -- multi-scale deformable attention gather (forward) and scatter (backward) for sm_100a.
+//
+// Replaces the reference kernels ms_deformable_im2col_gpu_kernel / ms_deformable_col2im_gpu_kernel_*
+// (lib/models/monodetr/ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299, 301-403) and their host
+// launchers (ms_deform_attn_cuda.cu:20-153).  Math: SURVEY.md appendix A.
+//
+// Data layout (all contiguous, owned by the caller):
+//   value  [B][S][M][D]      one (pixel, head) row is D floats = 128 B for D=32 -> one cache line
+//   loc    [B][Lq][M][L][P][2], attn [B][Lq][M][L][P], out [B][Lq][M*D]
+//
+// Fast path (fp32, D in {16,32,64}, P == 4, L <= 8): a "unit" is one (b, q, m).  D/4 lanes own a
+// unit, each lane owns 4 channels, so every bilinear corner is ONE 16-byte load per lane and one
+// fully coalesced 128-byte line per unit; a warp carries 32/(D/4) units = consecutive heads of one
+// query, so its output store is one contiguous 512-byte run.  All 16 corner loads of a level are
+// issued before use (ILP), sample coordinates are broadcast loads.
+// The backward pass keeps the same mapping, re-gathers the corners, scatters w*g*A with vector
+// reductions (red.global.add.v4.f32) and reduces d/dloc, d/dattn across the D/4 lanes with a
+// butterfly transpose-reduction (42 shuffles per unit instead of 144).
+//
+// Generic path (any D/L/P, fp32 and fp64): one warp per unit, lanes stride over channels.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/monodetr_b200.h"
+
+namespace {
+
+constexpr int kMaxLevels = 8;
+constexpr int kThreads = 256;
+
+struct LevelInfo {
+    int H[kMaxLevels];
+    int W[kMaxLevels];
+    int start[kMaxLevels];
+};
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float floor_t(float a) { return floorf(a); }
+__device__ __forceinline__ double floor_t(double a) { return floor(a); }
+
+// ------------------------------------------------------------------------------------------------
+// Fast forward: LPU lanes per unit, D = 4*LPU, P = 4.
+// ------------------------------------------------------------------------------------------------
+template <int LPU>
+__global__ void __launch_bounds__(kThreads)
+msda_fwd_vec_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                    const int64_t* __restrict__ lsi, const float* __restrict__ loc,
+                    const float* __restrict__ attn, int S, int M, int L, int Lq, long long n_units,
+                    float* __restrict__ out) {
+    constexpr int D = 4 * LPU;
+    constexpr int UPW = 32 / LPU;
+    constexpr int P = 4;
+    __shared__ LevelInfo lv;
+    if (threadIdx.x < L) {
+        lv.H[threadIdx.x] = (int)shapes[2 * threadIdx.x];
+        lv.W[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
+        lv.start[threadIdx.x] = (int)lsi[threadIdx.x];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPU;
+    const int cl = lane % LPU;
+    const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (kThreads / 32);
+    const int pix = M * D;  // floats between horizontally adjacent pixels
+
+    for (long long unit = warp * UPW + sub; unit < n_units; unit += nwarps * UPW) {
+        const int m = (int)(unit % M);
+        const long long b = unit / ((long long)Lq * M);
+        const float* vb = value + ((size_t)b * S * M + m) * D + cl * 4;
+        const float* lp = loc + (size_t)unit * L * P * 2;
+        const float* ap = attn + (size_t)unit * L * P;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        for (int l = 0; l < L; ++l) {
+            const int H = lv.H[l], W = lv.W[l];
+            const float* vl = vb + (size_t)lv.start[l] * pix;
+            const float4 xy01 = ldg4(lp + l * 8);
+            const float4 xy23 = ldg4(lp + l * 8 + 4);
+            const float4 a4 = ldg4(ap + l * 4);
+            const float xs[4] = {xy01.x, xy01.z, xy23.x, xy23.z};
+            const float ys[4] = {xy01.y, xy01.w, xy23.y, xy23.w};
+            const float as[4] = {a4.x, a4.y, a4.z, a4.w};
+            float4 v[P][4];
+            float w[P][4];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const float x = fmaf(xs[p], (float)W, -0.5f);
+                const float y = fmaf(ys[p], (float)H, -0.5f);
+                const bool inside = (y > -1.f) && (x > -1.f) && (y < (float)H) && (x < (float)W);
+                const float xf = floorf(x), yf = floorf(y);
+                const int x0 = (int)xf, y0 = (int)yf;
+                const float lx = x - xf, ly = y - yf, hx = 1.f - lx, hy = 1.f - ly;
+                const bool top = inside && (y0 >= 0), bot = inside && (y0 + 1 <= H - 1);
+                const bool lef = (x0 >= 0), rig = (x0 + 1 <= W - 1);
+                const float* p00 = vl + ((long long)y0 * W + x0) * pix;
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                v[p][0] = (top && lef) ? ldg4(p00) : z;
+                v[p][1] = (top && rig) ? ldg4(p00 + pix) : z;
+                v[p][2] = (bot && lef) ? ldg4(p00 + (long long)W * pix) : z;
+                v[p][3] = (bot && rig) ? ldg4(p00 + (long long)W * pix + pix) : z;
+                const float a = as[p];
+                w[p][0] = a * (hy * hx);
+                w[p][1] = a * (hy * lx);
+                w[p][2] = a * (ly * hx);
+                w[p][3] = a * (ly * lx);
+            }
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    acc.x = fmaf(w[p][k], v[p][k].x, acc.x);
+                    acc.y = fmaf(w[p][k], v[p][k].y, acc.y);
+                    acc.z = fmaf(w[p][k], v[p][k].z, acc.z);
+                    acc.w = fmaf(w[p][k], v[p][k].w, acc.w);
+                }
+            }
+        }
+        *reinterpret_cast<float4*>(out + (size_t)unit * D + cl * 4) = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast backward: LPU lanes per unit, D = 4*LPU, L = 4, P = 4 (3*L*P = 48 per-unit outputs).
+// ------------------------------------------------------------------------------------------------
+template <int LPU, int L>
+__global__ void __launch_bounds__(kThreads, 2)
+msda_bwd_vec_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                    const int64_t* __restrict__ lsi, const float* __restrict__ loc,
+                    const float* __restrict__ attn, const float* __restrict__ grad_out, int S, int M,
+                    int Lq, long long n_units, float* __restrict__ grad_value,
+                    float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
+    constexpr int D = 4 * LPU;
+    constexpr int UPW = 32 / LPU;
+    constexpr int P = 4;
+    constexpr int NLOC = 2 * L * P;      // grad_loc values per unit
+    constexpr int NV = 3 * L * P;        // + grad_attn values
+    constexpr int PER = NV / LPU;        // values a lane ends up owning
+    static_assert(NV % LPU == 0 && NLOC % LPU == 0, "butterfly needs divisibility");
+    __shared__ LevelInfo lv;
+    if (threadIdx.x < L) {
+        lv.H[threadIdx.x] = (int)shapes[2 * threadIdx.x];
+        lv.W[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
+        lv.start[threadIdx.x] = (int)lsi[threadIdx.x];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPU;
+    const int cl = lane % LPU;
+    const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (kThreads / 32);
+    const int pix = M * D;
+    const long long n_iter_units = ((n_units + UPW - 1) / UPW) * UPW;  // keep warps converged for shuffles
+
+    for (long long unit = warp * UPW + sub; unit < n_iter_units; unit += nwarps * UPW) {
+        const bool live = unit < n_units;
+        const long long u = live ? unit : 0;
+        const int m = (int)(u % M);
+        const long long b = u / ((long long)Lq * M);
+        const size_t vbase = ((size_t)b * S * M + m) * D + cl * 4;
+        const float* lp = loc + (size_t)u * L * P * 2;
+        const float* ap = attn + (size_t)u * L * P;
+        float4 g = ldg4(grad_out + (size_t)u * D + cl * 4);
+        if (!live) g = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        // vals[] is stored pre-permuted so that after the butterfly lane `cl` owns outputs
+        // j = i*LPU + cl (i = 0..PER-1): output j lives at position (j % LPU) * PER + j / LPU.
+        float vals[NV];
+#pragma unroll
+        for (int l = 0; l < L; ++l) {
+            const int H = lv.H[l], W = lv.W[l];
+            const size_t lbase = vbase + (size_t)lv.start[l] * pix;
+            const float4 xy01 = ldg4(lp + l * 8);
+            const float4 xy23 = ldg4(lp + l * 8 + 4);
+            const float4 a4 = ldg4(ap + l * 4);
+            const float xs[4] = {xy01.x, xy01.z, xy23.x, xy23.z};
+            const float ys[4] = {xy01.y, xy01.w, xy23.y, xy23.w};
+            const float as[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const float x = fmaf(xs[p], (float)W, -0.5f);
+                const float y = fmaf(ys[p], (float)H, -0.5f);
+                const bool inside = live && (y > -1.f) && (x > -1.f) && (y < (float)H) && (x < (float)W);
+                const float xf = floorf(x), yf = floorf(y);
+                const int x0 = (int)xf, y0 = (int)yf;
+                const float lx = x - xf, ly = y - yf, hx = 1.f - lx, hy = 1.f - ly;
+                const bool top = inside && (y0 >= 0), bot = inside && (y0 + 1 <= H - 1);
+                const bool lef = (x0 >= 0), rig = (x0 + 1 <= W - 1);
+                const long long o00 = (long long)lbase + ((long long)y0 * W + x0) * pix;
+                const long long o01 = o00 + pix, o10 = o00 + (long long)W * pix, o11 = o10 + pix;
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 v1 = (top && lef) ? ldg4(value + o00) : z;
+                const float4 v2 = (top && rig) ? ldg4(value + o01) : z;
+                const float4 v3 = (bot && lef) ? ldg4(value + o10) : z;
+                const float4 v4 = (bot && rig) ? ldg4(value + o11) : z;
+                const float a = as[p];
+                const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+                const float tx = g.x * a, ty = g.y * a, tz = g.z * a, tw = g.w * a;
+                if (top && lef) red_add_v4(grad_value + o00, w1 * tx, w1 * ty, w1 * tz, w1 * tw);
+                if (top && rig) red_add_v4(grad_value + o01, w2 * tx, w2 * ty, w2 * tz, w2 * tw);
+                if (bot && lef) red_add_v4(grad_value + o10, w3 * tx, w3 * ty, w3 * tz, w3 * tw);
+                if (bot && rig) red_add_v4(grad_value + o11, w4 * tx, w4 * ty, w4 * tz, w4 * tw);
+                // per-channel bilinear value and its x / y derivatives (cuh:123-158)
+                float ga = 0.f, gx = 0.f, gy = 0.f;
+#define MDB_ACC(c)                                                                   \
+    ga = fmaf(g.c, w1 * v1.c + w2 * v2.c + w3 * v3.c + w4 * v4.c, ga);               \
+    gx = fmaf(g.c * a, hy * (v2.c - v1.c) + ly * (v4.c - v3.c), gx);                 \
+    gy = fmaf(g.c * a, hx * (v3.c - v1.c) + lx * (v4.c - v2.c), gy);
+                MDB_ACC(x) MDB_ACC(y) MDB_ACC(z) MDB_ACC(w)
+#undef MDB_ACC
+                const int jx = (l * P + p) * 2, jy = jx + 1, ja = NLOC + l * P + p;
+                vals[(jx % LPU) * PER + jx / LPU] = gx * (float)W;
+                vals[(jy % LPU) * PER + jy / LPU] = gy * (float)H;
+                vals[(ja % LPU) * PER + ja / LPU] = ga;
+            }
+        }
+        // butterfly transpose-reduce across the LPU lanes of the unit
+        {
+            int n = NV;
+#pragma unroll
+            for (int off = LPU / 2; off >= 1; off >>= 1) {
+                n >>= 1;
+                const bool up = (cl & off) != 0;
+#pragma unroll
+                for (int i = 0; i < NV / 2; ++i) {
+                    if (i < n) {
+                        const float send = up ? vals[i] : vals[i + n];
+                        const float keep = up ? vals[i + n] : vals[i];
+                        vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                    }
+                }
+            }
+        }
+        if (live) {
+            float* gl = grad_loc + (size_t)unit * NLOC;
+            float* gat = grad_attn + (size_t)unit * (L * P);
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int j = i * LPU + cl;
+                if (i * LPU < NLOC) gl[j] = vals[i];
+                else gat[j - NLOC] = vals[i];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic kernels: one warp per unit, lanes stride over channels; any D, L, P; float and double.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+msda_fwd_generic_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
+                        const int64_t* __restrict__ lsi, const T* __restrict__ loc,
+                        const T* __restrict__ attn, int S, int M, int D, int L, int Lq, int P,
+                        long long n_units, T* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (kThreads / 32);
+    const size_t pix = (size_t)M * D;
+    for (long long unit = warp; unit < n_units; unit += nwarps) {
+        const int m = (int)(unit % M);
+        const long long b = unit / ((long long)Lq * M);
+        for (int c0 = 0; c0 < D; c0 += 32) {
+            const int c = c0 + lane;
+            const bool cok = c < D;
+            T acc = 0;
+            for (int l = 0; l < L; ++l) {
+                const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1];
+                const T* vl = value + ((size_t)b * S + (size_t)lsi[l]) * pix + (size_t)m * D + (cok ? c : 0);
+                for (int p = 0; p < P; ++p) {
+                    const size_t pi = ((size_t)unit * L + l) * P + p;
+                    const T a = attn[pi];
+                    const T x = fma_t(loc[2 * pi], (T)W, (T)-0.5);
+                    const T y = fma_t(loc[2 * pi + 1], (T)H, (T)-0.5);
+                    if (!(y > (T)-1 && x > (T)-1 && y < (T)H && x < (T)W)) continue;
+                    const T xf = floor_t(x), yf = floor_t(y);
+                    const int x0 = (int)xf, y0 = (int)yf;
+                    const T lx = x - xf, ly = y - yf, hx = (T)1 - lx, hy = (T)1 - ly;
+                    const bool top = y0 >= 0, bot = y0 + 1 <= H - 1, lef = x0 >= 0, rig = x0 + 1 <= W - 1;
+                    const long long o00 = ((long long)y0 * W + x0) * (long long)pix;
+                    T v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+                    if (cok) {
+                        if (top && lef) v1 = vl[o00];
+                        if (top && rig) v2 = vl[o00 + (long long)pix];
+                        if (bot && lef) v3 = vl[o00 + (long long)W * pix];
+                        if (bot && rig) v4 = vl[o00 + (long long)W * pix + pix];
+                    }
+                    acc += a * ((hy * hx) * v1 + (hy * lx) * v2 + (ly * hx) * v3 + (ly * lx) * v4);
+                }
+            }
+            if (cok) out[(size_t)unit * D + c] = acc;
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+msda_bwd_generic_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
+                        const int64_t* __restrict__ lsi, const T* __restrict__ loc,
+                        const T* __restrict__ attn, const T* __restrict__ grad_out, int S, int M, int D,
+                        int L, int Lq, int P, long long n_units, T* __restrict__ grad_value,
+                        T* __restrict__ grad_loc, T* __restrict__ grad_attn) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (kThreads / 32);
+    const size_t pix = (size_t)M * D;
+    for (long long unit = warp; unit < n_units; unit += nwarps) {
+        const int m = (int)(unit % M);
+        const long long b = unit / ((long long)Lq * M);
+        for (int l = 0; l < L; ++l) {
+            const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1];
+            const size_t lbase = ((size_t)b * S + (size_t)lsi[l]) * pix + (size_t)m * D;
+            for (int p = 0; p < P; ++p) {
+                const size_t pi = ((size_t)unit * L + l) * P + p;
+                const T a = attn[pi];
+                const T x = fma_t(loc[2 * pi], (T)W, (T)-0.5);
+                const T y = fma_t(loc[2 * pi + 1], (T)H, (T)-0.5);
+                T ga = 0, gx = 0, gy = 0;
+                if (y > (T)-1 && x > (T)-1 && y < (T)H && x < (T)W) {   // warp-uniform
+                    const T xf = floor_t(x), yf = floor_t(y);
+                    const int x0 = (int)xf, y0 = (int)yf;
+                    const T lx = x - xf, ly = y - yf, hx = (T)1 - lx, hy = (T)1 - ly;
+                    const bool top = y0 >= 0, bot = y0 + 1 <= H - 1, lef = x0 >= 0, rig = x0 + 1 <= W - 1;
+                    const long long o00 = (long long)lbase + ((long long)y0 * W + x0) * (long long)pix;
+                    const long long o01 = o00 + (long long)pix, o10 = o00 + (long long)W * pix, o11 = o10 + pix;
+                    for (int c = lane; c < D; c += 32) {
+                        const T g = grad_out[(size_t)unit * D + c];
+                        const T tg = g * a;
+                        T v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+                        if (top && lef) { v1 = value[o00 + c]; atomicAdd(grad_value + o00 + c, (hy * hx) * tg); }
+                        if (top && rig) { v2 = value[o01 + c]; atomicAdd(grad_value + o01 + c, (hy * lx) * tg); }
+                        if (bot && lef) { v3 = value[o10 + c]; atomicAdd(grad_value + o10 + c, (ly * hx) * tg); }
+                        if (bot && rig) { v4 = value[o11 + c]; atomicAdd(grad_value + o11 + c, (ly * lx) * tg); }
+                        ga += g * ((hy * hx) * v1 + (hy * lx) * v2 + (ly * hx) * v3 + (ly * lx) * v4);
+                        gx += tg * (hy * (v2 - v1) + ly * (v4 - v3));
+                        gy += tg * (hx * (v3 - v1) + lx * (v4 - v2));
+                    }
+                }
+                ga = warp_sum(ga);
+                gx = warp_sum(gx);
+                gy = warp_sum(gy);
+                if (lane == 0) {
+                    grad_attn[pi] = ga;
+                    grad_loc[2 * pi] = (T)W * gx;
+                    grad_loc[2 * pi + 1] = (T)H * gy;
+                }
+            }
+        }
+    }
+}
+
+int num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    }
+    return sms;
+}
+
+int grid_for(long long n_warps_needed, int blocks_per_sm) {
+    long long blocks = (n_warps_needed + (kThreads / 32) - 1) / (kThreads / 32);
+    const long long cap = (long long)num_sms() * blocks_per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+int check_common(const void* a, const void* b, const void* c, const void* d, const void* e, int B, int S,
+                 int M, int D, int L, int Lq, int P) {
+    if (B < 0 || S < 0 || M < 0 || D < 0 || L < 0 || Lq < 0 || P < 0) return MDB_EINVAL;
+    const long long n = (long long)B * Lq * M * D;
+    if (n > 0 && L > 0 && P > 0 && (!a || !b || !c || !d || !e)) return MDB_EINVAL;
+    return 0;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename T>
+int forward_impl(const T* value, const int64_t* shapes, const int64_t* lsi, const T* loc, const T* attn, int B,
+                 int S, int M, int D, int L, int Lq, int P, T* out, void* stream_) {
+    int rc = check_common(value, shapes, lsi, loc, attn, B, S, M, D, L, Lq, P);
+    if (rc) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const long long n_units = (long long)B * Lq * M;
+    if (n_units == 0 || D == 0) return 0;
+    if (!out) return MDB_EINVAL;
+    if (L == 0 || P == 0) {
+        return (int)cudaMemsetAsync(out, 0, sizeof(T) * (size_t)n_units * D, stream);
+    }
+    if constexpr (sizeof(T) == 4) {
+        const bool fast = (P == 4) && (L <= kMaxLevels) && (D == 16 || D == 32 || D == 64) && aligned16(value) &&
+                          aligned16(loc) && aligned16(attn) && aligned16(out);
+        if (fast) {
+            const int lpu = D / 4, upw = 32 / lpu;
+            const int grid = grid_for((n_units + upw - 1) / upw, 8);
+            if (lpu == 8)
+                msda_fwd_vec_kernel<8><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, S, M, L, Lq, n_units, out);
+            else if (lpu == 4)
+                msda_fwd_vec_kernel<4><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, S, M, L, Lq, n_units, out);
+            else
+                msda_fwd_vec_kernel<16><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, S, M, L, Lq, n_units, out);
+            return (int)cudaGetLastError();
+        }
+    }
+    const int grid = grid_for(n_units, 8);
+    msda_fwd_generic_kernel<T><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, S, M, D, L, Lq, P, n_units, out);
+    return (int)cudaGetLastError();
+}
+
+template <typename T>
+int backward_impl(const T* value, const int64_t* shapes, const int64_t* lsi, const T* loc, const T* attn,
+                  const T* grad_out, int B, int S, int M, int D, int L, int Lq, int P, T* grad_value, T* grad_loc,
+                  T* grad_attn, void* stream_) {
+    int rc = check_common(value, shapes, lsi, loc, attn, B, S, M, D, L, Lq, P);
+    if (rc) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const long long n_units = (long long)B * Lq * M;
+    const size_t nv = (size_t)B * S * M * D;
+    if (nv) {
+        if (!grad_value) return MDB_EINVAL;
+        cudaError_t e = cudaMemsetAsync(grad_value, 0, sizeof(T) * nv, stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (n_units == 0 || L == 0 || P == 0) return 0;
+    if (!grad_loc || !grad_attn) return MDB_EINVAL;
+    if (D == 0) {
+        cudaError_t e = cudaMemsetAsync(grad_loc, 0, sizeof(T) * (size_t)n_units * L * P * 2, stream);
+        if (e != cudaSuccess) return (int)e;
+        return (int)cudaMemsetAsync(grad_attn, 0, sizeof(T) * (size_t)n_units * L * P, stream);
+    }
+    if (!grad_out) return MDB_EINVAL;
+    if constexpr (sizeof(T) == 4) {
+        const bool fast = (P == 4) && (L == 4) && (D == 16 || D == 32 || D == 64) && aligned16(value) &&
+                          aligned16(loc) && aligned16(attn) && aligned16(grad_out) && aligned16(grad_value);
+        if (fast) {
+            const int lpu = D / 4, upw = 32 / lpu;
+            const int grid = grid_for((n_units + upw - 1) / upw, 6);
+            if (lpu == 8)
+                msda_bwd_vec_kernel<8, 4><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, grad_out, S, M, Lq, n_units, grad_value, grad_loc, grad_attn);
+            else if (lpu == 4)
+                msda_bwd_vec_kernel<4, 4><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, grad_out, S, M, Lq, n_units, grad_value, grad_loc, grad_attn);
+            else
+                msda_bwd_vec_kernel<16, 4><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, grad_out, S, M, Lq, n_units, grad_value, grad_loc, grad_attn);
+            return (int)cudaGetLastError();
+        }
+    }
+    const int grid = grid_for(n_units, 8);
+    msda_bwd_generic_kernel<T><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, grad_out, S, M, D, L, Lq, P, n_units, grad_value, grad_loc, grad_attn);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+int mdb_msda_forward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                         const float* sampling_loc, const float* attn_weight, int B, int S, int M, int D, int L,
+                         int Lq, int P, float* out, void* stream) {
+    return forward_impl<float>(value, spatial_shapes, level_start, sampling_loc, attn_weight, B, S, M, D, L, Lq, P, out, stream);
+}
+int mdb_msda_forward_f64(const double* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                         const double* sampling_loc, const double* attn_weight, int B, int S, int M, int D, int L,
+                         int Lq, int P, double* out, void* stream) {
+    return forward_impl<double>(value, spatial_shapes, level_start, sampling_loc, attn_weight, B, S, M, D, L, Lq, P, out, stream);
+}
+int mdb_msda_backward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                          const float* sampling_loc, const float* attn_weight, const float* grad_out, int B, int S,
+                          int M, int D, int L, int Lq, int P, float* grad_value, float* grad_loc, float* grad_attn,
+                          void* stream) {
+    return backward_impl<float>(value, spatial_shapes, level_start, sampling_loc, attn_weight, grad_out, B, S, M, D, L, Lq, P, grad_value, grad_loc, grad_attn, stream);
+}
+int mdb_msda_backward_f64(const double* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                          const double* sampling_loc, const double* attn_weight, const double* grad_out, int B, int S,
+                          int M, int D, int L, int Lq, int P, double* grad_value, double* grad_loc, double* grad_attn,
+                          void* stream) {
+    return backward_impl<double>(value, spatial_shapes, level_start, sampling_loc, attn_weight, grad_out, B, S, M, D, L, Lq, P, grad_value, grad_loc, grad_attn, stream);
+}
+
+}  // extern "C"
