@@ -60,6 +60,35 @@ int mdb_msda_backward_f64(const double* value, const int64_t* spatial_shapes, co
                           int B, int S, int M, int D, int L, int Lq, int P,
                           double* grad_value, double* grad_loc, double* grad_attn, void* stream);
 
+/* ---- Tensor-core convolution / linear family (tcgen05 + TMEM + TMA, fp32 storage, TF32 math) ----
+ * Replaces the cuDNN / cuBLAS calls behind nn.Conv2d / nn.Linear on the reference path
+ * (backbone.py:100-102; monodetr.py:83-91; depth_predictor/depth_predictor.py:29-47;
+ *  ops/modules/ms_deform_attn.py:138-161; depthaware_transformer.py:339-343,467-473).
+ * Activations are NHWC fp32: x[B][H][W][Cin], y[B][Ho][Wo][Cout]; weights are "packed"
+ * [kh*kw][Cout][Cin] (mdb_pack_conv_weight_f32).  A linear layer y[M,N] = x[M,K] w[N,K]^T is the call
+ * with B=1, H=1, W=M, Cin=K, Cout=N, kh=kw=1, stride=1, pad=0 (w itself is already "packed").
+ * Supported: kh=kw in {1,3}, stride in {1,2}, Cin%4==0, Cout%4==0, 16-byte aligned pointers.
+ */
+int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* bias /*[Cout]|NULL*/,
+                           const float* residual /*like y|NULL*/, float* y,
+                           int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
+                           int relu, void* stream);
+/* dx = (conv_transpose(dy, w) + residual) * (relu_mask > 0); residual / relu_mask are shaped like dx or NULL. */
+int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* residual, const float* relu_mask,
+                         float* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
+                         void* stream);
+/* dw_packed[tap][Cout][Cin] (+)= rowscale[co] * sum dy * x ; zero-filled first unless accumulate. */
+int mdb_conv2d_wgrad_f32(const float* dy, const float* x, const float* rowscale /*[Cout]|NULL*/, float* dw_packed,
+                         int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
+                         int accumulate, void* stream);
+/* w_packed[t][o][i] = w_oihw[o][i][t] * (scale ? scale[o] : 1)   (FrozenBatchNorm fold, backbone.py:54-64) */
+int mdb_pack_conv_weight_f32(const float* w_oihw, const float* scale, float* w_packed, int O, int I, int taps,
+                             void* stream);
+int mdb_unpack_conv_wgrad_f32(const float* dw_packed, float* dw_oihw, int O, int I, int taps, int accumulate,
+                              void* stream);
+/* out[n] (+)= sum_m x[m][n]  (bias gradients) */
+int mdb_colsum_f32(const float* x, float* out, long long M, int N, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,522 @@
+// conv_gemm.cu -- tcgen05 / TMEM / TMA implicit-GEMM kernel family for sm_100a (fp32 storage, TF32
+// tensor-core math, fp32 accumulate in TMEM).  One kernel template serves
+//   * linear layers and 1x1 convolutions (a GEMM is a 1-tap convolution over a 1-row image),
+//   * KxK convolutions, im2col-free: for every filter tap the TMA engine fetches the SHIFTED
+//     NHWC activation box (out-of-bounds = zero fill = padding; element strides = conv stride),
+//   * their data gradients (same kernel, B operand read MN-major straight from the packed weights),
+//   * their weight gradients (both operands MN-major straight from dY / X, split-K with vector reds).
+// It replaces the cuDNN / cuBLAS calls behind nn.Conv2d / nn.Linear on the reference path
+// (lib/models/monodetr/backbone.py:100-102 torchvision ResNet-50 convs; monodetr.py:83-91 input_proj;
+// depth_predictor/depth_predictor.py:29-47; ops/modules/ms_deform_attn.py:138-161 projections;
+// depthaware_transformer.py:339-343,467-473 FFN / decoder linears).
+//
+// Layouts: activations NHWC fp32 [B][H][W][C]; packed weights [tap][Cout][Cin]; output NHWC.
+// Tile: 128 output pixels (a th x tw rectangle of one image) x BN output channels, K step = 32 fp32
+// (one 128-byte swizzle span).  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
+// issuer (one elected lane), warps 2-5 = epilogue (TMEM -> registers -> fused bias / residual /
+// ReLU / ReLU-mask / row-scale -> global).  smem ring of STAGES stages, mbarrier full/empty pairs.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/monodetr_b200.h"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace mdb;
+
+constexpr int BM = 128;
+constexpr int BK = 32;                 // fp32 elements per k-block = 128 bytes
+constexpr int kTileABytes = BM * 128;  // 16 KiB
+constexpr int kChunkBytes = 32 * 128;  // one MN-major chunk: 32 reduction rows x 128 B
+constexpr int kThreadsTC = 192;
+constexpr int kMaxTaps = 9;
+
+struct TcParams {
+    // ---- fprop / dgrad: decomposition of the M dimension into th x tw pixel rectangles ----------
+    int tiles_x, tiles_y, tw, th;
+    int Ho, Wo;                      // logical output grid covered by tiles (bounds for rows)
+    int out_sy, out_sx, out_oy, out_ox, out_H, out_W;   // real output pixel = (y*out_sy+out_oy, ...)
+    int in_sy, in_sx;                // A-box origin = (y0*in_sy + dy[tap], x0*in_sx + dx[tap])
+    int ntaps, cblocks;
+    int tap_dy[kMaxTaps], tap_dx[kMaxTaps], tap_w[kMaxTaps];
+    // ---- wgrad: reduction over pixel tiles of 32 (rth x rtw), split across blockIdx.z ----------
+    int rtiles_x, rtiles_y, rtw, rth, n_img, red_per_split;
+    int w_dy, w_dx, w_sy, w_sx;      // X-box origin = (y0*w_sy + w_dy, x0*w_sx + w_dx)  (per launch = per tap)
+    // ---- epilogue -----------------------------------------------------------------------------
+    int Mo_rows;                     // wgrad: number of valid output rows (Cout)
+    int No, ldo;
+    int relu, atomic_out;
+    const float* bias;               // [No] or null
+    const float* residual;           // same indexing as out, or null
+    const float* relu_mask;          // same indexing as out: out *= (mask > 0), or null
+    const float* rowscale;           // wgrad: [Mo_rows] or null
+    float* out;
+};
+
+template <int BN, int STAGES, int MODE /*0 fprop/dgrad, 1 wgrad*/, bool B_MN>
+__global__ void __launch_bounds__(kThreadsTC)
+tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    const __grid_constant__ TcParams p) {
+    constexpr bool A_MN = (MODE == 1);
+    constexpr int kTileBBytes = BN * 128;
+    constexpr int kStageBytes = kTileABytes + kTileBBytes;
+    static_assert(!(MODE == 1) || B_MN, "wgrad reads both operands MN-major");
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // ---- tile coordinates ------------------------------------------------------------------------
+    const int n0 = blockIdx.x * BN;          // output-column tile
+    int img = 0, y0 = 0, x0 = 0, m0 = 0, red_begin = 0, red_end = 0, total_iters = 0;
+    if constexpr (MODE == 0) {
+        int t = blockIdx.y;
+        const int per_img = p.tiles_x * p.tiles_y;
+        img = t / per_img;
+        t -= img * per_img;
+        y0 = (t / p.tiles_x) * p.th;
+        x0 = (t % p.tiles_x) * p.tw;
+        total_iters = p.ntaps * p.cblocks;
+    } else {
+        m0 = blockIdx.y * BM;                // output rows = Cout
+        const int total_red = p.n_img * p.rtiles_x * p.rtiles_y;
+        red_begin = blockIdx.z * p.red_per_split;
+        red_end = min(total_red, red_begin + p.red_per_split);
+        total_iters = max(0, red_end - red_begin);
+    }
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapB);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer =============================================
+        if (elect_one()) {
+            for (int it = 0; it < total_iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* a_dst = smem + s * kStageBytes;
+                uint8_t* b_dst = a_dst + kTileABytes;
+                mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                if constexpr (MODE == 0) {
+                    const int tap = it / p.cblocks;
+                    const int cb = it - tap * p.cblocks;
+                    tma_load_4d(a_dst, &mapA, &full_bar[s], cb * BK, x0 * p.in_sx + p.tap_dx[tap],
+                                y0 * p.in_sy + p.tap_dy[tap], img);
+                    if constexpr (!B_MN) {
+                        tma_load_3d(b_dst, &mapB, &full_bar[s], cb * BK, n0, p.tap_w[tap]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 32; ++j)
+                            tma_load_3d(b_dst + j * kChunkBytes, &mapB, &full_bar[s], n0 + j * 32, cb * BK, p.tap_w[tap]);
+                    }
+                } else {
+                    int r = red_begin + it;
+                    const int per_img = p.rtiles_x * p.rtiles_y;
+                    const int ri = r / per_img;
+                    r -= ri * per_img;
+                    const int ry = (r / p.rtiles_x) * p.rth;
+                    const int rx = (r % p.rtiles_x) * p.rtw;
+#pragma unroll
+                    for (int j = 0; j < BM / 32; ++j)
+                        tma_load_4d(a_dst + j * kChunkBytes, &mapA, &full_bar[s], m0 + j * 32, rx, ry, ri);
+#pragma unroll
+                    for (int j = 0; j < BN / 32; ++j)
+                        tma_load_4d(b_dst + j * kChunkBytes, &mapB, &full_bar[s], n0 + j * 32, rx * p.w_sx + p.w_dx,
+                                    ry * p.w_sy + p.w_dy, ri);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==============================================
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_tf32(BM, BN, A_MN, B_MN);
+            for (int it = 0; it < total_iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
+                const uint32_t b_addr = a_addr + kTileABytes;
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    // K-major: 8 fp32 = 32 B further along the 128-B swizzle row; rows 8 apart = 1024 B (SBO).
+                    // MN-major: 8 reduction rows = 1024 B further; 32-wide MN chunks 4096 B apart (LBO).
+                    const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_addr + k * 1024, kChunkBytes, 1024)
+                                                : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+                    const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_addr + k * 1024, kChunkBytes, 1024)
+                                                : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                    umma_tf32(tmem_base, adesc, bdesc, idesc, (it > 0) || (k > 0));
+                }
+                umma_commit(&empty_bar[s]);    // frees the smem stage when these MMAs retire
+            }
+            umma_commit(tmem_full);            // accumulator complete
+        }
+    } else {
+        // ================================ epilogue =================================================
+        const int q = warp & 3;                // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        bool row_ok;
+        size_t out_row;                        // element offset of (row, column 0) in out / residual / mask
+        float rscale = 1.f;
+        if constexpr (MODE == 0) {
+            const int ly = row / p.tw, lx = row - ly * p.tw;
+            const int y = y0 + ly, x = x0 + lx;
+            row_ok = (y < p.Ho) && (x < p.Wo);
+            const int oy = y * p.out_sy + p.out_oy, ox = x * p.out_sx + p.out_ox;
+            out_row = (((size_t)img * p.out_H + oy) * p.out_W + ox) * (size_t)p.ldo;
+        } else {
+            row_ok = (m0 + row) < p.Mo_rows;
+            out_row = (size_t)(m0 + row) * p.ldo;
+            if (row_ok && p.rowscale) rscale = p.rowscale[m0 + row];
+        }
+        if (total_iters > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+        }
+        const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (n0 + c0 >= p.No) break;        // uniform across the CTA
+            uint32_t r[32];
+            if (total_iters > 0) {
+                tmem_ld_32x32(taddr_row + c0, r);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+            if (!row_ok) continue;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const int n = n0 + c0 + j;
+                if (n >= p.No) break;
+                float v[4] = {__uint_as_float(r[j]) * rscale, __uint_as_float(r[j + 1]) * rscale,
+                              __uint_as_float(r[j + 2]) * rscale, __uint_as_float(r[j + 3]) * rscale};
+                const size_t o = out_row + n;
+                if (n + 3 < p.No) {
+                    if (p.bias) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                        v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+                    }
+                    if (p.residual) {
+                        const float4 b = *reinterpret_cast<const float4*>(p.residual + o);
+                        v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+                    }
+                    if (p.relu_mask) {
+                        const float4 b = *reinterpret_cast<const float4*>(p.relu_mask + o);
+                        v[0] = b.x > 0.f ? v[0] : 0.f; v[1] = b.y > 0.f ? v[1] : 0.f;
+                        v[2] = b.z > 0.f ? v[2] : 0.f; v[3] = b.w > 0.f ? v[3] : 0.f;
+                    }
+                    if (p.atomic_out) red_add_v4_f32(p.out + o, v[0], v[1], v[2], v[3]);
+                    else *reinterpret_cast<float4*>(p.out + o) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+                    for (int e = 0; e < 4 && n + e < p.No; ++e) {
+                        float x = v[e];
+                        if (p.bias) x += p.bias[n + e];
+                        if (p.residual) x += p.residual[o + e];
+                        if (p.relu) x = fmaxf(x, 0.f);
+                        if (p.relu_mask) x = p.relu_mask[o + e] > 0.f ? x : 0.f;
+                        if (p.atomic_out) atomicAdd(p.out + o + e, x);
+                        else p.out[o + e] = x;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<BN>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    return fn;
+}
+
+// dims/strides innermost first; strides in ELEMENTS for dims 1..rank-1 (dim 0 is contiguous).
+int make_map(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+             const uint32_t* box, const uint32_t* estr) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return MDB_EUNSUPPORTED;
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = estr ? estr[i] : 1;
+    }
+    for (int i = 1; i < rank; ++i) {
+        gstr[i - 1] = strides_elems[i] * sizeof(float);
+        if (gstr[i - 1] % 16) return MDB_EINVAL;
+    }
+    if (reinterpret_cast<uintptr_t>(base) % 16) return MDB_EINVAL;
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : MDB_EINVAL;
+}
+
+template <int BN, int STAGES, int MODE, bool B_MN>
+int launch_tc(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t stream) {
+    constexpr int smem = STAGES * (kTileABytes + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
+    static bool configured = false;
+    auto kern = tc_conv_gemm_kernel<BN, STAGES, MODE, B_MN>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    kern<<<grid, kThreadsTC, smem, stream>>>(a, b, p);
+    return (int)cudaGetLastError();
+}
+
+// choose a th x tw rectangle with th*tw == n_pix (128 for M tiles, 32 for wgrad reduction tiles)
+void pick_tile(int W, int H, int n_pix, int* tw, int* th) {
+    int best_tw = n_pix, best_waste = 1 << 30;
+    for (int w = n_pix; w >= 1; w >>= 1) {
+        const int h = n_pix / w;
+        const int tx = (W + w - 1) / w, ty = (H + h - 1) / h;
+        const int waste = tx * w * ty * h - W * H;
+        if (waste < best_waste) { best_waste = waste; best_tw = w; }
+    }
+    *tw = best_tw;
+    *th = n_pix / best_tw;
+}
+
+struct ConvGeom {
+    int B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo;
+};
+
+int check_geom(const ConvGeom& g) {
+    if (g.B <= 0 || g.H <= 0 || g.W <= 0 || g.Cin <= 0 || g.Cout <= 0) return MDB_EINVAL;
+    if (g.kh != g.kw || (g.kh != 1 && g.kh != 3) || (g.stride != 1 && g.stride != 2)) return MDB_EUNSUPPORTED;
+    if (g.Cin % 4 || g.Cout % 4) return MDB_EUNSUPPORTED;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// y[B,Ho,Wo,Cout] = act( conv(x[B,H,W,Cin], w_packed[kh*kw][Cout][Cin]) + bias + residual )
+int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
+                           int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int relu,
+                           void* stream_) {
+    ConvGeom g{B, H, W, Cin, Cout, kh, kw, stride, pad, (H + 2 * pad - kh) / stride + 1, (W + 2 * pad - kw) / stride + 1};
+    int rc = check_geom(g);
+    if (rc) return rc;
+    if (!x || !w_packed || !y) return MDB_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    pick_tile(g.Wo, g.Ho, BM, &p.tw, &p.th);
+    p.tiles_x = (g.Wo + p.tw - 1) / p.tw;
+    p.tiles_y = (g.Ho + p.th - 1) / p.th;
+    p.Ho = g.Ho; p.Wo = g.Wo;
+    p.out_sy = p.out_sx = 1; p.out_oy = p.out_ox = 0; p.out_H = g.Ho; p.out_W = g.Wo;
+    p.in_sy = p.in_sx = stride;
+    p.ntaps = kh * kw;
+    p.cblocks = (Cin + BK - 1) / BK;
+    for (int ky = 0; ky < kh; ++ky)
+        for (int kx = 0; kx < kw; ++kx) {
+            const int t = ky * kw + kx;
+            p.tap_dy[t] = ky - pad; p.tap_dx[t] = kx - pad; p.tap_w[t] = t;
+        }
+    p.No = Cout; p.ldo = Cout; p.relu = relu; p.atomic_out = 0;
+    p.bias = bias; p.residual = residual; p.relu_mask = nullptr; p.rowscale = nullptr; p.out = y;
+
+    CUtensorMap ma, mb;
+    {   // A: x as (C, W, H, B), box (32, tw*s, th*s, 1), element strides (1, s, s, 1)
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+        uint64_t str[4] = {1, (uint64_t)Cin, (uint64_t)W * Cin, (uint64_t)H * W * Cin};
+        uint32_t box[4] = {BK, (uint32_t)(p.tw * stride), (uint32_t)(p.th * stride), 1};
+        uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+        if (box[1] > 256 || box[2] > 256) return MDB_EUNSUPPORTED;
+        rc = make_map(&ma, x, 4, dims, str, box, es);
+        if (rc) return rc;
+    }
+    const bool wide = (Cout >= 256) && ((long long)B * p.tiles_x * p.tiles_y * (Cout / 256) >= 120);
+    const int bn = wide ? 256 : 128;
+    {   // B: packed weights as (Cin, Cout, taps), box (32, BN, 1)
+        uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
+        uint64_t str[3] = {1, (uint64_t)Cin, (uint64_t)Cout * Cin};
+        uint32_t box[3] = {BK, (uint32_t)bn, 1};
+        rc = make_map(&mb, w_packed, 3, dims, str, box, nullptr);
+        if (rc) return rc;
+    }
+    dim3 grid((Cout + bn - 1) / bn, B * p.tiles_x * p.tiles_y, 1);
+    if (wide) return launch_tc<256, 4, 0, false>(ma, mb, p, grid, stream);
+    return launch_tc<128, 3, 0, false>(ma, mb, p, grid, stream);
+}
+
+// dx[B,H,W,Cin] = (conv_transpose(dy[B,Ho,Wo,Cout], w_packed) + residual) * (relu_mask > 0)
+int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* residual, const float* relu_mask,
+                         float* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
+                         void* stream_) {
+    ConvGeom g{B, H, W, Cin, Cout, kh, kw, stride, pad, (H + 2 * pad - kh) / stride + 1, (W + 2 * pad - kw) / stride + 1};
+    int rc = check_geom(g);
+    if (rc) return rc;
+    if (!dy || !w_packed || !dx) return MDB_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    // dx[y,x] = sum_{ky,kx} dy[(y+pad-ky)/s, (x+pad-kx)/s] * W[ky,kx]  where the division is exact.
+    // Per output parity class (py,px) (only one class for s == 1) the contributing taps are fixed and the
+    // dy access is a unit-stride shifted box: oy = (y + pad - ky)/s = j + (py + pad - ky)/s  for y = s*j + py.
+    for (int py = 0; py < stride; ++py)
+        for (int px = 0; px < stride; ++px) {
+            TcParams p;
+            memset(&p, 0, sizeof(p));
+            const int Hc = (H - py + stride - 1) / stride, Wc = (W - px + stride - 1) / stride;  // pixels in class
+            if (Hc <= 0 || Wc <= 0) continue;
+            pick_tile(Wc, Hc, BM, &p.tw, &p.th);
+            p.tiles_x = (Wc + p.tw - 1) / p.tw;
+            p.tiles_y = (Hc + p.th - 1) / p.th;
+            p.Ho = Hc; p.Wo = Wc;
+            p.out_sy = p.out_sx = stride; p.out_oy = py; p.out_ox = px; p.out_H = H; p.out_W = W;
+            p.in_sy = p.in_sx = 1;
+            p.cblocks = (Cout + BK - 1) / BK;
+            int nt = 0;
+            for (int ky = 0; ky < kh; ++ky) {
+                if ((py + pad - ky) % stride) continue;
+                for (int kx = 0; kx < kw; ++kx) {
+                    if ((px + pad - kx) % stride) continue;
+                    // floor division is exact here (numerator divisible by stride; may be negative)
+                    p.tap_dy[nt] = (py + pad - ky) / stride;
+                    p.tap_dx[nt] = (px + pad - kx) / stride;
+                    p.tap_w[nt] = ky * kw + kx;
+                    ++nt;
+                }
+            }
+            p.ntaps = nt;
+            p.No = Cin; p.ldo = Cin; p.relu = 0; p.atomic_out = 0;
+            p.bias = nullptr; p.residual = residual; p.relu_mask = relu_mask; p.rowscale = nullptr; p.out = dx;
+            CUtensorMap ma, mb;
+            {   // A: dy as (Cout, Wo, Ho, B), unit stride
+                uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)B};
+                uint64_t str[4] = {1, (uint64_t)Cout, (uint64_t)g.Wo * Cout, (uint64_t)g.Ho * g.Wo * Cout};
+                uint32_t box[4] = {BK, (uint32_t)p.tw, (uint32_t)p.th, 1};
+                rc = make_map(&ma, dy, 4, dims, str, box, nullptr);
+                if (rc) return rc;
+            }
+            {   // B (MN-major): packed weights as (Cin, Cout, taps); box = 32 output columns (Cin) x 32 reduction rows (Cout)
+                uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
+                uint64_t str[3] = {1, (uint64_t)Cin, (uint64_t)Cout * Cin};
+                uint32_t box[3] = {32, 32, 1};
+                rc = make_map(&mb, w_packed, 3, dims, str, box, nullptr);
+                if (rc) return rc;
+            }
+            dim3 grid((Cin + 127) / 128, B * p.tiles_x * p.tiles_y, 1);
+            if (nt == 0) {   // no tap reaches this parity class (1x1 stride 2): result = (0 + residual) * mask
+                p.ntaps = 0;
+            }
+            rc = launch_tc<128, 3, 0, true>(ma, mb, p, grid, stream);
+            if (rc) return rc;
+        }
+    return 0;
+}
+
+// dw_packed[tap][Cout][Cin] (+)= rowscale[co] * sum_{b,oy,ox} dy[b,oy,ox,co] * x[b, oy*s+ky-pad, ox*s+kx-pad, ci]
+// dw_packed is zero-filled by the call unless accumulate != 0.
+int mdb_conv2d_wgrad_f32(const float* dy, const float* x, const float* rowscale, float* dw_packed, int B, int H, int W,
+                         int Cin, int Cout, int kh, int kw, int stride, int pad, int accumulate, void* stream_) {
+    ConvGeom g{B, H, W, Cin, Cout, kh, kw, stride, pad, (H + 2 * pad - kh) / stride + 1, (W + 2 * pad - kw) / stride + 1};
+    int rc = check_geom(g);
+    if (rc) return rc;
+    if (!dy || !x || !dw_packed) return MDB_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int taps = kh * kw;
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(dw_packed, 0, sizeof(float) * (size_t)taps * Cout * Cin, stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    pick_tile(g.Wo, g.Ho, 32, &p.rtw, &p.rth);
+    p.rtiles_x = (g.Wo + p.rtw - 1) / p.rtw;
+    p.rtiles_y = (g.Ho + p.rth - 1) / p.rth;
+    p.n_img = B;
+    const int total_red = B * p.rtiles_x * p.rtiles_y;
+    const int bn = (Cin >= 256) ? 256 : 128;
+    const int tiles = ((Cout + BM - 1) / BM) * ((Cin + bn - 1) / bn) * taps;
+    int splits = (296 + tiles - 1) / tiles;            // aim at ~2 waves of 148 SMs
+    if (splits > total_red) splits = total_red;
+    if (splits < 1) splits = 1;
+    p.red_per_split = (total_red + splits - 1) / splits;
+    splits = (total_red + p.red_per_split - 1) / p.red_per_split;
+    p.w_sy = p.w_sx = stride;
+    p.Mo_rows = Cout; p.No = Cin; p.ldo = Cin; p.relu = 0; p.atomic_out = 1;
+    p.bias = nullptr; p.residual = nullptr; p.relu_mask = nullptr; p.rowscale = rowscale;
+
+    CUtensorMap ma, mb;
+    {   // A (MN-major): dy as (Cout, Wo, Ho, B); box = 32 channels x (rtw x rth) reduction pixels
+        uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)B};
+        uint64_t str[4] = {1, (uint64_t)Cout, (uint64_t)g.Wo * Cout, (uint64_t)g.Ho * g.Wo * Cout};
+        uint32_t box[4] = {32, (uint32_t)p.rtw, (uint32_t)p.rth, 1};
+        rc = make_map(&ma, dy, 4, dims, str, box, nullptr);
+        if (rc) return rc;
+    }
+    {   // B (MN-major): x as (Cin, W, H, B) with element strides s
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+        uint64_t str[4] = {1, (uint64_t)Cin, (uint64_t)W * Cin, (uint64_t)H * W * Cin};
+        uint32_t box[4] = {32, (uint32_t)(p.rtw * stride), (uint32_t)(p.rth * stride), 1};
+        uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+        rc = make_map(&mb, x, 4, dims, str, box, es);
+        if (rc) return rc;
+    }
+    for (int t = 0; t < taps; ++t) {
+        p.w_dy = t / kw - pad;
+        p.w_dx = t % kw - pad;
+        p.out = dw_packed + (size_t)t * Cout * Cin;
+        dim3 grid((Cin + bn - 1) / bn, (Cout + BM - 1) / BM, splits);
+        rc = (bn == 256) ? launch_tc<256, 4, 1, true>(ma, mb, p, grid, stream)
+                         : launch_tc<128, 3, 1, true>(ma, mb, p, grid, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // extern "C"

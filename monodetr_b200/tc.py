@@ -1,0 +1,122 @@
+"""Host wrappers of the tensor-core convolution / linear C ABI (include/monodetr_b200.h, "Tensor-core
+convolution / linear family").  Tensors are fp32 CUDA, activations NHWC, weights packed [tap][Cout][Cin].
+No fallback: a missing library or a failing launch raises RuntimeError.
+"""
+import torch
+
+from . import _lib
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("monodetr_b200.tc: CUDA tensors required (no CPU path)")
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError("monodetr_b200.tc: contiguous float32 tensors required")
+
+
+def out_size(n, k, s, p):
+    return (n + 2 * p - k) // s + 1
+
+
+def pack_weight(w_oihw, scale=None):
+    """(O, I, kh, kw) -> (kh*kw, O, I), optionally multiplied by scale[O] (FrozenBatchNorm fold)."""
+    _chk(w_oihw, scale)
+    O, I, kh, kw = w_oihw.shape
+    out = torch.empty((kh * kw, O, I), dtype=torch.float32, device=w_oihw.device)
+    _lib.check(_lib.lib().mdb_pack_conv_weight_f32(_p(w_oihw), _p(scale), _p(out), O, I, kh * kw, _s()), "pack_weight")
+    _lib.count(1)
+    return out
+
+
+def unpack_wgrad(dw_packed, kh, kw):
+    _chk(dw_packed)
+    taps, O, I = dw_packed.shape
+    out = torch.empty((O, I, kh, kw), dtype=torch.float32, device=dw_packed.device)
+    _lib.check(_lib.lib().mdb_unpack_conv_wgrad_f32(_p(dw_packed), _p(out), O, I, taps, 0, _s()), "unpack_wgrad")
+    _lib.count(1)
+    return out
+
+
+def colsum(x2d):
+    _chk(x2d)
+    M, N = x2d.shape
+    out = torch.empty((N,), dtype=torch.float32, device=x2d.device)
+    _lib.check(_lib.lib().mdb_colsum_f32(_p(x2d), _p(out), M, N, 0, _s()), "colsum")
+    _lib.count(1)
+    return out
+
+
+def conv2d_forward(x, w_packed, bias=None, residual=None, kh=1, kw=1, stride=1, pad=0, relu=False):
+    _chk(x, w_packed, bias, residual)
+    B, H, W, Cin = x.shape
+    taps, Cout, Cin2 = w_packed.shape
+    assert taps == kh * kw and Cin2 == Cin
+    Ho, Wo = out_size(H, kh, stride, pad), out_size(W, kw, stride, pad)
+    y = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+    if residual is not None:
+        assert residual.shape == y.shape
+    rc = _lib.lib().mdb_conv2d_forward_f32(_p(x), _p(w_packed), _p(bias), _p(residual), _p(y), B, H, W, Cin, Cout, kh, kw,
+                                           stride, pad, int(relu), _s())
+    _lib.check(rc, "conv2d_forward")
+    _lib.count(1)
+    return y
+
+
+def conv2d_dgrad(dy, w_packed, x_shape, residual=None, relu_mask=None, kh=1, kw=1, stride=1, pad=0):
+    _chk(dy, w_packed, residual, relu_mask)
+    B, H, W, Cin = x_shape
+    taps, Cout, Cin2 = w_packed.shape
+    assert Cin2 == Cin and dy.shape[-1] == Cout
+    dx = torch.empty((B, H, W, Cin), dtype=torch.float32, device=dy.device)
+    rc = _lib.lib().mdb_conv2d_dgrad_f32(_p(dy), _p(w_packed), _p(residual), _p(relu_mask), _p(dx), B, H, W, Cin, Cout, kh,
+                                         kw, stride, pad, _s())
+    _lib.check(rc, "conv2d_dgrad")
+    _lib.count(stride * stride)
+    return dx
+
+
+def conv2d_wgrad(dy, x, rowscale=None, kh=1, kw=1, stride=1, pad=0):
+    _chk(dy, x, rowscale)
+    B, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    dwp = torch.empty((kh * kw, Cout, Cin), dtype=torch.float32, device=x.device)
+    rc = _lib.lib().mdb_conv2d_wgrad_f32(_p(dy), _p(x), _p(rowscale), _p(dwp), B, H, W, Cin, Cout, kh, kw, stride, pad, 0,
+                                         _s())
+    _lib.check(rc, "conv2d_wgrad")
+    _lib.count(kh * kw)
+    return dwp
+
+
+# ---- linear layers = 1x1 convolution over a 1-row "image" of M pixels ---------------------------------
+def linear_forward(x2d, w, bias=None, residual=None, relu=False):
+    M, K = x2d.shape
+    N = w.shape[0]
+    y = conv2d_forward(x2d.view(1, 1, M, K), w.view(1, N, K), bias, None if residual is None else residual.view(1, 1, M, N),
+                       relu=relu)
+    return y.view(M, N)
+
+
+def linear_dgrad(dy2d, w, residual=None, relu_mask=None):
+    M, N = dy2d.shape
+    K = w.shape[1]
+    dx = conv2d_dgrad(dy2d.view(1, 1, M, N), w.view(1, N, K), (1, 1, M, K),
+                      None if residual is None else residual.view(1, 1, M, K),
+                      None if relu_mask is None else relu_mask.view(1, 1, M, K))
+    return dx.view(M, K)
+
+
+def linear_wgrad(dy2d, x2d):
+    M, N = dy2d.shape
+    K = x2d.shape[1]
+    return conv2d_wgrad(dy2d.view(1, 1, M, N), x2d.view(1, 1, M, K)).view(N, K)

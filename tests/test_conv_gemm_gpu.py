@@ -1,0 +1,115 @@
+"""GPU numerics of the tcgen05 implicit-GEMM family against a plain PyTorch fp32 reference of the same op
+(TF32 disabled in the reference).  Tolerance: TF32 inputs (10-bit mantissa), fp32 accumulate ->
+max|err| <= 2e-3 * max|ref| per op (the end-to-end 1e-3 budget is checked on the model outputs)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-3
+
+
+def _ref_setup():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def _relerr(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
+
+
+def _report(name, a, b):
+    err = _relerr(a, b)
+    print(f"{name}: rel err {err:.3e}  max|ref| {float(b.abs().max()):.3e}")
+    return err
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 256), (1000, 256, 256), (10200, 256, 256), (4400, 128, 256),
+                                   (333, 24, 256), (550, 4, 256), (81600, 256, 256), (2048, 1024, 512), (777, 512, 2048)])
+def test_linear_forward(M, N, K):
+    from monodetr_b200 import tc
+    _ref_setup()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    r = torch.randn(M, N, device="cuda", generator=g)
+    y = tc.linear_forward(x, w)
+    assert _report("plain", y, x @ w.t()) < TOL
+    y = tc.linear_forward(x, w, b, r, relu=True)
+    assert _report("bias+res+relu", y, torch.relu(x @ w.t() + b + r)) < TOL
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (1000, 256, 256), (10200, 256, 256), (4400, 128, 256), (550, 4, 256),
+                                   (3000, 1024, 512)])
+def test_linear_backward(M, N, K):
+    from monodetr_b200 import tc
+    _ref_setup()
+    g = torch.Generator(device="cuda").manual_seed(M * 3 + N + K)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    dy = torch.randn(M, N, device="cuda", generator=g)
+    res = torch.randn(M, K, device="cuda", generator=g)
+    dx = tc.linear_dgrad(dy, w)
+    assert _report("dgrad", dx, dy @ w) < TOL
+    dx = tc.linear_dgrad(dy, w, residual=res, relu_mask=x)
+    assert _report("dgrad+res+mask", dx, (dy @ w + res) * (x > 0)) < TOL
+    dw = tc.linear_wgrad(dy, x)
+    assert _report("wgrad", dw, dy.t() @ x) < TOL
+    db = tc.colsum(dy)
+    assert _report("colsum", db, dy.sum(0)) < 1e-4
+
+
+CONVS = [
+    # B, H, W, Cin, Cout, k, stride, pad
+    (2, 24, 80, 256, 256, 3, 1, 1),
+    (2, 48, 160, 128, 128, 3, 1, 1),
+    (2, 96, 320, 128, 128, 3, 2, 1),
+    (2, 12, 40, 512, 512, 3, 1, 1),
+    (2, 12, 40, 2048, 256, 3, 2, 1),
+    (1, 48, 160, 256, 256, 3, 2, 1),
+    (2, 96, 320, 256, 512, 1, 2, 0),
+    (2, 24, 80, 1024, 2048, 1, 2, 0),
+    (2, 13, 37, 64, 68, 3, 1, 1),          # ragged everything
+    (1, 7, 9, 32, 36, 3, 2, 1),            # odd sizes with stride 2
+    (2, 96, 320, 64, 256, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("cfg", CONVS)
+def test_conv_forward_backward(cfg):
+    from monodetr_b200 import tc
+    _ref_setup()
+    B, H, W, Cin, Cout, k, s, pad = cfg
+    g = torch.Generator(device="cuda").manual_seed(sum(cfg))
+    x = torch.randn(B, Cin, H, W, device="cuda", generator=g)
+    w = torch.randn(Cout, Cin, k, k, device="cuda", generator=g) / (Cin * k * k) ** 0.5
+    scale = torch.rand(Cout, device="cuda", generator=g) + 0.5
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    wp = tc.pack_weight(w, scale)
+    ref_wp = (w * scale.view(-1, 1, 1, 1)).permute(2, 3, 0, 1).reshape(k * k, Cout, Cin)
+    assert torch.equal(wp, ref_wp.contiguous())
+    ws = w * scale.view(-1, 1, 1, 1)
+    ref = F.conv2d(x, ws, bias, stride=s, padding=pad)
+    res = torch.randn_like(ref)
+    y = tc.conv2d_forward(x_nhwc, wp, bias, None, k, k, s, pad, relu=False)
+    assert _report("fwd", y.permute(0, 3, 1, 2), ref) < TOL
+    y = tc.conv2d_forward(x_nhwc, wp, bias, res.permute(0, 2, 3, 1).contiguous(), k, k, s, pad, relu=True)
+    assert _report("fwd+res+relu", y.permute(0, 3, 1, 2), torch.relu(ref + res)) < TOL
+    # backward
+    dy = torch.randn_like(ref)
+    dy_nhwc = dy.permute(0, 2, 3, 1).contiguous()
+    xr = x.clone().requires_grad_(True)
+    wr = ws.clone().requires_grad_(True)
+    F.conv2d(xr, wr, None, stride=s, padding=pad).backward(dy)
+    dx = tc.conv2d_dgrad(dy_nhwc, wp, x_nhwc.shape, None, None, k, k, s, pad)
+    assert _report("dgrad", dx.permute(0, 3, 1, 2), xr.grad) < TOL
+    mask = torch.randn_like(x_nhwc)
+    res2 = torch.randn_like(x_nhwc)
+    dx = tc.conv2d_dgrad(dy_nhwc, wp, x_nhwc.shape, res2, mask, k, k, s, pad)
+    assert _report("dgrad+res+mask", dx, (xr.grad.permute(0, 2, 3, 1) + res2) * (mask > 0)) < TOL
+    dwp = tc.conv2d_wgrad(dy_nhwc, x_nhwc, scale, k, k, s, pad)
+    dw = tc.unpack_wgrad(dwp, k, k)
+    assert _report("wgrad", dw, wr.grad * scale.view(-1, 1, 1, 1)) < TOL
