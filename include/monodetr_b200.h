@@ -89,6 +89,45 @@ int mdb_unpack_conv_wgrad_f32(const float* dw_packed, float* dw_oihw, int O, int
 /* out[n] (+)= sum_m x[m][n]  (bias gradients) */
 int mdb_colsum_f32(const float* x, float* out, long long M, int N, int accumulate, void* stream);
 
+/* ---- Fused multi-head attention core, head_dim 32 (attention.cu) -------------------------------------
+ * Replaces the core of torch's F.multi_head_attention_forward as called at depthaware_transformer.py:456-459,
+ * :496 and depth_predictor/transformer.py:59.  q[b][i][h][32] with token stride ldq floats (batch stride
+ * Lq*ldq), k/v likewise (Lk*ldk, Lk*ldv), out[b][i][h*32] with token stride ldo.  key_padding_mask [B][Lk]
+ * bytes (nonzero = ignore) or NULL.  lse [B][H][Lq] is written by forward and read by backward.
+ * Dropout on the probabilities: drop_p in [0,1); *seed is read on the device (CUDA-graph safe); `site`
+ * decorrelates call sites.  delta_ws: B*H*Lq floats of workspace.
+ */
+int mdb_attention_forward_f32(const float* q, const float* k, const float* v, const unsigned char* key_padding_mask,
+                              float* out, float* lse, int B, int H, int Lq, int Lk, int head_dim,
+                              int ldq, int ldk, int ldv, int ldo, float drop_p,
+                              const unsigned long long* seed, unsigned long long site, void* stream);
+int mdb_attention_backward_f32(const float* q, const float* k, const float* v, const unsigned char* key_padding_mask,
+                               const float* out, const float* lse, const float* dout, float* delta_ws,
+                               float* dq, float* dk, float* dv, int B, int H, int Lq, int Lk, int head_dim,
+                               int ldq, int ldk, int ldv, int ldo, int lddq, int lddk, int lddv, float drop_p,
+                               const unsigned long long* seed, unsigned long long site, void* stream);
+
+/* ---- Normalisation (norm.cu) ---------------------------------------------------------------------------
+ * y = LayerNorm(x + dropout(res)) * gamma + beta, rows of C floats (C in {128,256,512}); res may be NULL.
+ * Replaces the `src = norm(src + dropout(src2))` pattern of depthaware_transformer.py:341-349,461-462,502-513
+ * and depth_predictor/transformer.py:60-65.  mean / rstd: [M] saved for backward.
+ * backward: dx = grad wrt x (and wrt res when drop_p == 0); dres (may be NULL iff drop_p == 0) = grad wrt res.
+ */
+int mdb_add_layernorm_forward_f32(const float* x, const float* res, const float* gamma, const float* beta, float* y,
+                                  float* mean, float* rstd, long long M, int C, float eps, float drop_p,
+                                  const unsigned long long* seed, unsigned long long site, void* stream);
+int mdb_add_layernorm_backward_f32(const float* dy, const float* x, const float* res, const float* gamma,
+                                   const float* mean, const float* rstd, float* dx, float* dres, float* dgamma,
+                                   float* dbeta, long long M, int C, float drop_p, const unsigned long long* seed,
+                                   unsigned long long site, int accumulate, void* stream);
+/* GroupNorm(G, C) on NHWC x[B][HW][C] (+ optional fused ReLU) -- monodetr.py:83-91, depth_predictor.py:29-45.
+ * stats_ws: B*G*2 doubles; mean / rstd: [B][G]. */
+int mdb_groupnorm_forward_f32(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                              double* stats_ws, int B, int HW, int C, int G, float eps, int relu, void* stream);
+int mdb_groupnorm_backward_f32(const float* dy, const float* x, const float* y, const float* gamma, const float* mean,
+                               const float* rstd, float* dx, float* dgamma, float* dbeta, double* stats_ws,
+                               int B, int HW, int C, int G, int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

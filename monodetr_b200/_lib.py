@@ -26,6 +26,12 @@ SIGNATURES = {
     "mdb_pack_conv_weight_f32": [_PTR] * 3 + [c_int] * 3 + [_PTR],
     "mdb_unpack_conv_wgrad_f32": [_PTR] * 2 + [c_int] * 4 + [_PTR],
     "mdb_colsum_f32": [_PTR] * 2 + [ctypes.c_longlong, c_int, c_int, _PTR],
+    "mdb_attention_forward_f32": [_PTR] * 6 + [c_int] * 9 + [c_float, _PTR, ctypes.c_ulonglong, _PTR],
+    "mdb_attention_backward_f32": [_PTR] * 11 + [c_int] * 12 + [c_float, _PTR, ctypes.c_ulonglong, _PTR],
+    "mdb_add_layernorm_forward_f32": [_PTR] * 7 + [ctypes.c_longlong, c_int, c_float, c_float, _PTR, ctypes.c_ulonglong, _PTR],
+    "mdb_add_layernorm_backward_f32": [_PTR] * 10 + [ctypes.c_longlong, c_int, c_float, _PTR, ctypes.c_ulonglong, c_int, _PTR],
+    "mdb_groupnorm_forward_f32": [_PTR] * 7 + [c_int] * 4 + [c_float, c_int, _PTR],
+    "mdb_groupnorm_backward_f32": [_PTR] * 10 + [c_int] * 5 + [_PTR],
 }
 _RESTYPES = {"mdb_error_string": ctypes.c_char_p}
 

@@ -162,12 +162,13 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 const uint32_t b_addr = a_addr + kTileABytes;
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k) {
-                    // K-major: 8 fp32 = 32 B further along the 128-B swizzle row; rows 8 apart = 1024 B (SBO).
-                    // MN-major: 8 reduction rows = 1024 B further; 32-wide MN chunks 4096 B apart (LBO).
-                    const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_addr + k * 1024, kChunkBytes, 1024)
-                                                : make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-                    const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_addr + k * 1024, kChunkBytes, 1024)
-                                                : make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+                    // K-major (SWIZZLE_128B): 8 fp32 = 32 B further along the 128-B row; 8-row groups 1024 B apart (SBO).
+                    // MN-major (128B swizzle, 32-B atoms, 4-row period): 8 reduction rows = 1024 B further per k-step;
+                    // 4-row groups 512 B apart (SBO); 32-wide MN chunks 4096 B apart (LBO).
+                    const uint64_t adesc = A_MN ? make_smem_desc(a_addr + k * 1024, kChunkBytes, 512, 1)
+                                                : make_smem_desc(a_addr + k * 32, 16, 1024, 2);
+                    const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * 1024, kChunkBytes, 512, 1)
+                                                : make_smem_desc(b_addr + k * 32, 16, 1024, 2);
                     umma_tf32(tmem_base, adesc, bdesc, idesc, (it > 0) || (k > 0));
                 }
                 umma_commit(&empty_bar[s]);    // frees the smem stage when these MMAs retire
@@ -280,7 +281,7 @@ EncodeTiledFn get_encode() {
 
 // dims/strides innermost first; strides in ELEMENTS for dims 1..rank-1 (dim 0 is contiguous).
 int make_map(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-             const uint32_t* box, const uint32_t* estr) {
+             const uint32_t* box, const uint32_t* estr, bool mn_major = false) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return MDB_EUNSUPPORTED;
     cuuint64_t gdim[5], gstr[4];
@@ -296,7 +297,9 @@ int make_map(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, 
     }
     if (reinterpret_cast<uintptr_t>(base) % 16) return MDB_EINVAL;
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : MDB_EINVAL;
 }
@@ -446,7 +449,7 @@ int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* re
                 uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
                 uint64_t str[3] = {1, (uint64_t)Cin, (uint64_t)Cout * Cin};
                 uint32_t box[3] = {32, 32, 1};
-                rc = make_map(&mb, w_packed, 3, dims, str, box, nullptr);
+                rc = make_map(&mb, w_packed, 3, dims, str, box, nullptr, true);
                 if (rc) return rc;
             }
             dim3 grid((Cin + 127) / 128, B * p.tiles_x * p.tiles_y, 1);
@@ -496,7 +499,7 @@ int mdb_conv2d_wgrad_f32(const float* dy, const float* x, const float* rowscale,
         uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)B};
         uint64_t str[4] = {1, (uint64_t)Cout, (uint64_t)g.Wo * Cout, (uint64_t)g.Ho * g.Wo * Cout};
         uint32_t box[4] = {32, (uint32_t)p.rtw, (uint32_t)p.rth, 1};
-        rc = make_map(&ma, dy, 4, dims, str, box, nullptr);
+        rc = make_map(&ma, dy, 4, dims, str, box, nullptr, true);
         if (rc) return rc;
     }
     {   // B (MN-major): x as (Cin, W, H, B) with element strides s
@@ -504,7 +507,7 @@ int mdb_conv2d_wgrad_f32(const float* dy, const float* x, const float* rowscale,
         uint64_t str[4] = {1, (uint64_t)Cin, (uint64_t)W * Cin, (uint64_t)H * W * Cin};
         uint32_t box[4] = {32, (uint32_t)(p.rtw * stride), (uint32_t)(p.rth * stride), 1};
         uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
-        rc = make_map(&mb, x, 4, dims, str, box, es);
+        rc = make_map(&mb, x, 4, dims, str, box, es, true);
         if (rc) return rc;
     }
     for (int t = 0; t < taps; ++t) {

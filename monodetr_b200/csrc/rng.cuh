@@ -1,0 +1,33 @@
+// rng.cuh -- counter-based hash RNG for dropout masks.  mask(seed, index) is a pure function, so the
+// backward pass regenerates exactly the mask the forward pass used (no mask tensors in HBM), and the
+// seed lives in device memory so a captured CUDA graph sees a fresh value every replay.
+#pragma once
+#include <stdint.h>
+
+namespace mdb {
+
+__host__ __device__ __forceinline__ uint64_t fmix64(uint64_t x) {   // MurmurHash3 finalizer
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+
+// uniform in [0, 1) with 24 bits of resolution
+__host__ __device__ __forceinline__ float rng_uniform(uint64_t seed, uint64_t idx) {
+    const uint64_t h = fmix64(idx * 0x9E3779B97F4A7C15ull + seed);
+    return (float)(uint32_t)(h >> 40) * (1.0f / 16777216.0f);
+}
+
+// four independent uniforms for indices 4*quad .. 4*quad+3 from one hash (16 bits each)
+__host__ __device__ __forceinline__ void rng_uniform4(uint64_t seed, uint64_t quad, float (&u)[4]) {
+    const uint64_t h = fmix64(quad * 0x9E3779B97F4A7C15ull + seed);
+    u[0] = (float)(uint32_t)(h & 0xFFFF) * (1.0f / 65536.0f);
+    u[1] = (float)(uint32_t)((h >> 16) & 0xFFFF) * (1.0f / 65536.0f);
+    u[2] = (float)(uint32_t)((h >> 32) & 0xFFFF) * (1.0f / 65536.0f);
+    u[3] = (float)(uint32_t)((h >> 48) & 0xFFFF) * (1.0f / 65536.0f);
+}
+
+}  // namespace mdb

@@ -136,9 +136,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---- descriptors ------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (64 bit): [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4,
 // [46,48) version=1 (Blackwell), [61,64) layout (2 = SWIZZLE_128B).
-__host__ __device__ constexpr uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout: 2 = SWIZZLE_128B (16-byte chunks, 8-row period; K-major operands),
+//         1 = SWIZZLE_128B with 32-byte atoms (4-row period) -- the ONLY layout tcgen05 accepts for MN-major
+//             32-bit (tf32) operands; TMA side: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+__host__ __device__ constexpr uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                      uint32_t layout) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
+}
+__host__ __device__ constexpr uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return make_smem_desc(smem_addr, lbo_bytes, sbo_bytes, 2);
 }
 // Instruction descriptor (32 bit) for kind::tf32, fp32 accumulate:
 // [4,6) c_format=1(F32), [7,10) a_format=2(TF32), [10,13) b_format=2, [15] a_major (1 = MN), [16] b_major,
