@@ -72,16 +72,16 @@ int mdb_msda_backward_f64(const double* value, const int64_t* spatial_shapes, co
 int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* bias /*[Cout]|NULL*/,
                            const float* residual /*like y|NULL*/, float* y,
                            int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
-                           int relu, void* stream);
+                           int flags /* bit0: ReLU, bit1: store y rounded-to-nearest TF32 */, void* stream);
 /* dx = (conv_transpose(dy, w) + residual) * (relu_mask > 0); residual / relu_mask are shaped like dx or NULL. */
 int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* residual, const float* relu_mask,
                          float* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
-                         void* stream);
+                         int flags /* bit1: store dx rounded-to-nearest TF32 */, void* stream);
 /* dw_packed[tap][Cout][Cin] (+)= rowscale[co] * sum dy * x ; zero-filled first unless accumulate. */
 int mdb_conv2d_wgrad_f32(const float* dy, const float* x, const float* rowscale /*[Cout]|NULL*/, float* dw_packed,
                          int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
                          int accumulate, void* stream);
-/* w_packed[t][o][i] = w_oihw[o][i][t] * (scale ? scale[o] : 1)   (FrozenBatchNorm fold, backbone.py:54-64) */
+/* w_packed[t][o][i] = rn_tf32( w_oihw[o][i][t] * (scale ? scale[o] : 1) )   (FrozenBatchNorm fold, backbone.py:54-64) */
 int mdb_pack_conv_weight_f32(const float* w_oihw, const float* scale, float* w_packed, int O, int I, int taps,
                              void* stream);
 int mdb_unpack_conv_wgrad_f32(const float* dw_packed, float* dw_oihw, int O, int I, int taps, int accumulate,
@@ -127,6 +127,17 @@ int mdb_groupnorm_forward_f32(const float* x, const float* gamma, const float* b
 int mdb_groupnorm_backward_f32(const float* dy, const float* x, const float* y, const float* gamma, const float* mean,
                                const float* rstd, float* dx, float* dgamma, float* dbeta, double* stats_ws,
                                int B, int HW, int C, int G, int relu, void* stream);
+
+/* ---- Elementwise helpers and the frozen ResNet stem (elementwise.cu) ------------------------------------ */
+int mdb_relu_backward_f32(const float* dy, const float* y, float* out, long long n, float scale, void* stream);
+int mdb_dropout_f32(const float* x, float* out, long long n, float p, const unsigned long long* seed,
+                    unsigned long long site, void* stream);
+int mdb_round_tf32_f32(const float* x, float* out, long long n, void* stream);
+/* backbone.py:100-102 conv1 + bn1 (FrozenBatchNorm2d, backbone.py:54-64) + relu; x NCHW [B][3][H][W] -> y NHWC [B][H/2][W/2][64] */
+int mdb_stem_conv7x7_bn_relu_f32(const float* x, const float* w, const float* scale, const float* bias, float* y,
+                                 int B, int H, int W, void* stream);
+/* torchvision ResNet maxpool(3, 2, 1) on NHWC */
+int mdb_maxpool3x3s2_nhwc_f32(const float* x, float* y, int B, int H, int W, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ SIGNATURES = {
     "mdb_msda_backward_f32": [_PTR] * 6 + [c_int] * 7 + [_PTR] * 4,
     "mdb_msda_backward_f64": [_PTR] * 6 + [c_int] * 7 + [_PTR] * 4,
     "mdb_conv2d_forward_f32": [_PTR] * 5 + [c_int] * 10 + [_PTR],
-    "mdb_conv2d_dgrad_f32": [_PTR] * 5 + [c_int] * 9 + [_PTR],
+    "mdb_conv2d_dgrad_f32": [_PTR] * 5 + [c_int] * 10 + [_PTR],
     "mdb_conv2d_wgrad_f32": [_PTR] * 4 + [c_int] * 10 + [_PTR],
     "mdb_pack_conv_weight_f32": [_PTR] * 3 + [c_int] * 3 + [_PTR],
     "mdb_unpack_conv_wgrad_f32": [_PTR] * 2 + [c_int] * 4 + [_PTR],
@@ -32,6 +32,11 @@ SIGNATURES = {
     "mdb_add_layernorm_backward_f32": [_PTR] * 10 + [ctypes.c_longlong, c_int, c_float, _PTR, ctypes.c_ulonglong, c_int, _PTR],
     "mdb_groupnorm_forward_f32": [_PTR] * 7 + [c_int] * 4 + [c_float, c_int, _PTR],
     "mdb_groupnorm_backward_f32": [_PTR] * 10 + [c_int] * 5 + [_PTR],
+    "mdb_relu_backward_f32": [_PTR] * 3 + [ctypes.c_longlong, c_float, _PTR],
+    "mdb_dropout_f32": [_PTR] * 2 + [ctypes.c_longlong, c_float, _PTR, ctypes.c_ulonglong, _PTR],
+    "mdb_round_tf32_f32": [_PTR] * 2 + [ctypes.c_longlong, _PTR],
+    "mdb_stem_conv7x7_bn_relu_f32": [_PTR] * 5 + [c_int] * 3 + [_PTR],
+    "mdb_maxpool3x3s2_nhwc_f32": [_PTR] * 2 + [c_int] * 4 + [_PTR],
 }
 _RESTYPES = {"mdb_error_string": ctypes.c_char_p}
 

@@ -48,7 +48,7 @@ struct TcParams {
     // ---- epilogue -----------------------------------------------------------------------------
     int Mo_rows;                     // wgrad: number of valid output rows (Cout)
     int No, ldo;
-    int relu, atomic_out;
+    int relu, atomic_out, round_out;   // round_out: store round-to-nearest TF32 (next consumer is a tensor-core operand)
     const float* bias;               // [No] or null
     const float* residual;           // same indexing as out, or null
     const float* relu_mask;          // same indexing as out: out *= (mask > 0), or null
@@ -235,6 +235,10 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         v[0] = b.x > 0.f ? v[0] : 0.f; v[1] = b.y > 0.f ? v[1] : 0.f;
                         v[2] = b.z > 0.f ? v[2] : 0.f; v[3] = b.w > 0.f ? v[3] : 0.f;
                     }
+                    if (p.round_out) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[e] = round_tf32(v[e]);
+                    }
                     if (p.atomic_out) red_add_v4_f32(p.out + o, v[0], v[1], v[2], v[3]);
                     else *reinterpret_cast<float4*>(p.out + o) = make_float4(v[0], v[1], v[2], v[3]);
                 } else {
@@ -244,6 +248,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         if (p.residual) x += p.residual[o + e];
                         if (p.relu) x = fmaxf(x, 0.f);
                         if (p.relu_mask) x = p.relu_mask[o + e] > 0.f ? x : 0.f;
+                        if (p.round_out) x = round_tf32(x);
                         if (p.atomic_out) atomicAdd(p.out + o + e, x);
                         else p.out[o + e] = x;
                     }
@@ -348,7 +353,7 @@ extern "C" {
 
 // y[B,Ho,Wo,Cout] = act( conv(x[B,H,W,Cin], w_packed[kh*kw][Cout][Cin]) + bias + residual )
 int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
-                           int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int relu,
+                           int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int flags,
                            void* stream_) {
     ConvGeom g{B, H, W, Cin, Cout, kh, kw, stride, pad, (H + 2 * pad - kh) / stride + 1, (W + 2 * pad - kw) / stride + 1};
     int rc = check_geom(g);
@@ -370,7 +375,7 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
             const int t = ky * kw + kx;
             p.tap_dy[t] = ky - pad; p.tap_dx[t] = kx - pad; p.tap_w[t] = t;
         }
-    p.No = Cout; p.ldo = Cout; p.relu = relu; p.atomic_out = 0;
+    p.No = Cout; p.ldo = Cout; p.relu = flags & 1; p.round_out = (flags >> 1) & 1; p.atomic_out = 0;
     p.bias = bias; p.residual = residual; p.relu_mask = nullptr; p.rowscale = nullptr; p.out = y;
 
     CUtensorMap ma, mb;
@@ -400,7 +405,7 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
 // dx[B,H,W,Cin] = (conv_transpose(dy[B,Ho,Wo,Cout], w_packed) + residual) * (relu_mask > 0)
 int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* residual, const float* relu_mask,
                          float* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
-                         void* stream_) {
+                         int flags, void* stream_) {
     ConvGeom g{B, H, W, Cin, Cout, kh, kw, stride, pad, (H + 2 * pad - kh) / stride + 1, (W + 2 * pad - kw) / stride + 1};
     int rc = check_geom(g);
     if (rc) return rc;
@@ -435,7 +440,7 @@ int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* re
                 }
             }
             p.ntaps = nt;
-            p.No = Cin; p.ldo = Cin; p.relu = 0; p.atomic_out = 0;
+            p.No = Cin; p.ldo = Cin; p.relu = 0; p.atomic_out = 0; p.round_out = (flags >> 1) & 1;
             p.bias = nullptr; p.residual = residual; p.relu_mask = relu_mask; p.rowscale = nullptr; p.out = dx;
             CUtensorMap ma, mb;
             {   // A: dy as (Cout, Wo, Ho, B), unit stride

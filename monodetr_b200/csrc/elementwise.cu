@@ -19,7 +19,9 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
         const int t = (int)(r / O);
         float v = w[((size_t)o * I + ci) * taps + t];
         if (scale) v *= scale[o];
-        out[i] = v;
+        uint32_t rb;   // round-to-nearest TF32: the packed weights are tensor-core operands (tcgen05 truncates)
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rb) : "f"(v));
+        out[i] = __uint_as_float(rb);
     }
 }
 
@@ -94,6 +96,205 @@ int mdb_colsum_f32(const float* x, float* out, long long M, int N, int accumulat
     if (gy < 1) gy = 1;
     const int rows = (int)((M + gy - 1) / gy);
     colsum_kernel<<<dim3(gx, gy), 256, 0, stream>>>(x, out, M, N, rows);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// More HBM-bound helpers: ReLU backward mask, dropout (forward == backward kernel), TF32 rounding,
+// and the frozen ResNet stem (conv 7x7/2 + FrozenBN + ReLU, max-pool 3x3/2) -- backbone.py:71-73 keeps
+// conv1/layer1 frozen, so the stem only ever runs forward.
+// =================================================================================================
+#include "rng.cuh"
+
+namespace {
+
+__global__ void relu_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ y, float4* __restrict__ out,
+                                long long n4, float scale) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 d = dy[i], v = y[i];
+        out[i] = make_float4(v.x > 0.f ? d.x * scale : 0.f, v.y > 0.f ? d.y * scale : 0.f, v.z > 0.f ? d.z * scale : 0.f,
+                             v.w > 0.f ? d.w * scale : 0.f);
+    }
+}
+
+__global__ void dropout_kernel(const float4* __restrict__ x, float4* __restrict__ out, long long n4, float p,
+                               const unsigned long long* __restrict__ seed_ptr, unsigned long long site) {
+    const unsigned long long seed = *seed_ptr + site * 0x9E3779B97F4A7C15ull;
+    const float inv = 1.f / (1.f - p);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float u[4];
+        mdb::rng_uniform4(seed, (unsigned long long)i, u);
+        const float4 v = x[i];
+        out[i] = make_float4(u[0] >= p ? v.x * inv : 0.f, u[1] >= p ? v.y * inv : 0.f, u[2] >= p ? v.z * inv : 0.f,
+                             u[3] >= p ? v.w * inv : 0.f);
+    }
+}
+
+__device__ __forceinline__ float round_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+__global__ void round_tf32_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = round_tf32(x[i]);
+}
+
+// ---- stem: y[b][oy][ox][64] = relu(scale[c] * conv7x7s2(x NCHW [b][3][H][W]) + bias[c]) ----------------
+// CTA = 8 x 32 output pixels, 256 threads, one pixel per thread, 64 accumulators per thread.
+constexpr int ST_TH = 8, ST_TW = 32, ST_C = 64, ST_K = 7;
+constexpr int ST_IH = ST_TH * 2 + 5, ST_IW = ST_TW * 2 + 5;   // 21 x 69 input patch per channel
+
+__global__ void __launch_bounds__(256)
+stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][3][7][7]*/, const float* __restrict__ scale,
+                 const float* __restrict__ bias, float* __restrict__ y, int H, int W, int Ho, int Wo) {
+    extern __shared__ float sm[];
+    float* s_w = sm;                          // [147][64]  (tap-major so a tap's 64 weights are contiguous)
+    float* s_in = sm + 147 * ST_C;            // [3][21][69]
+    const int b = blockIdx.z;
+    const int oy0 = blockIdx.y * ST_TH, ox0 = blockIdx.x * ST_TW;
+    for (int i = threadIdx.x; i < 147 * ST_C; i += 256) {
+        const int c = i % ST_C, t = i / ST_C;
+        s_w[i] = w[c * 147 + t];
+    }
+    const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+    for (int i = threadIdx.x; i < 3 * ST_IH * ST_IW; i += 256) {
+        const int xx = i % ST_IW, r = i / ST_IW;
+        const int yy = r % ST_IH, ch = r / ST_IH;
+        const int gy = iy0 + yy, gx = ix0 + xx;
+        s_in[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? x[(((size_t)b * 3 + ch) * H + gy) * W + gx] : 0.f;
+    }
+    __syncthreads();
+    const int ly = threadIdx.x / ST_TW, lx = threadIdx.x % ST_TW;
+    float acc[ST_C];
+#pragma unroll
+    for (int c = 0; c < ST_C; ++c) acc[c] = 0.f;
+    for (int ch = 0; ch < 3; ++ch)
+        for (int ky = 0; ky < ST_K; ++ky) {
+            const float* row = s_in + (ch * ST_IH + ly * 2 + ky) * ST_IW + lx * 2;
+#pragma unroll
+            for (int kx = 0; kx < ST_K; ++kx) {
+                const float v = row[kx];
+                const float4* wp = reinterpret_cast<const float4*>(s_w + ((ch * ST_K + ky) * ST_K + kx) * ST_C);
+#pragma unroll
+                for (int c4 = 0; c4 < ST_C / 4; ++c4) {
+                    const float4 ww = wp[c4];
+                    acc[c4 * 4] = fmaf(v, ww.x, acc[c4 * 4]);
+                    acc[c4 * 4 + 1] = fmaf(v, ww.y, acc[c4 * 4 + 1]);
+                    acc[c4 * 4 + 2] = fmaf(v, ww.z, acc[c4 * 4 + 2]);
+                    acc[c4 * 4 + 3] = fmaf(v, ww.w, acc[c4 * 4 + 3]);
+                }
+            }
+        }
+    const int oy = oy0 + ly, ox = ox0 + lx;
+    if (oy < Ho && ox < Wo) {
+        float* yp = y + (((size_t)b * Ho + oy) * Wo + ox) * ST_C;
+#pragma unroll
+        for (int c4 = 0; c4 < ST_C / 4; ++c4) {
+            const float4 s = *reinterpret_cast<const float4*>(scale + c4 * 4);
+            const float4 bb = *reinterpret_cast<const float4*>(bias + c4 * 4);
+            float4 o;
+            o.x = fmaxf(fmaf(acc[c4 * 4], s.x, bb.x), 0.f);
+            o.y = fmaxf(fmaf(acc[c4 * 4 + 1], s.y, bb.y), 0.f);
+            o.z = fmaxf(fmaf(acc[c4 * 4 + 2], s.z, bb.z), 0.f);
+            o.w = fmaxf(fmaf(acc[c4 * 4 + 3], s.w, bb.w), 0.f);
+            o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
+            *reinterpret_cast<float4*>(yp + c4 * 4) = o;
+        }
+    }
+}
+
+// NHWC max-pool 3x3 stride 2 pad 1
+__global__ void maxpool3x3s2_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C, int Ho,
+                                    int Wo) {
+    const long long n4 = (long long)B * Ho * Wo * C / 4;
+    const int c4n = C / 4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % c4n);
+        long long r = i / c4n;
+        const int ox = (int)(r % Wo); r /= Wo;
+        const int oy = (int)(r % Ho);
+        const int b = (int)(r / Ho);
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oy * 2 - 1 + ky;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = ox * 2 - 1 + kx;
+                if (ix < 0 || ix >= W) continue;
+                const float4 v = *reinterpret_cast<const float4*>(x + (((size_t)b * H + iy) * W + ix) * C + c4 * 4);
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            }
+        }
+        *reinterpret_cast<float4*>(y + i * 4) = m;
+    }
+}
+
+int ew_grid2(long long n, int threads) {
+    long long g = (n + threads - 1) / threads;
+    if (g > 148 * 16) g = 148 * 16;
+    return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace
+
+extern "C" {
+
+// out = dy * (y > 0) * scale          (n % 4 == 0, 16-byte aligned)
+int mdb_relu_backward_f32(const float* dy, const float* y, float* out, long long n, float scale, void* stream) {
+    if (!dy || !y || !out || n < 0 || n % 4) return MDB_EINVAL;
+    if (n == 0) return 0;
+    relu_bwd_kernel<<<ew_grid2(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y), reinterpret_cast<float4*>(out), n / 4, scale);
+    return (int)cudaGetLastError();
+}
+
+// out = x * keep(seed, site, index) / (1 - p): the same call regenerates the mask for the backward pass.
+int mdb_dropout_f32(const float* x, float* out, long long n, float p, const unsigned long long* seed,
+                    unsigned long long site, void* stream) {
+    if (!x || !out || !seed || n < 0 || n % 4 || p < 0.f || p >= 1.f) return MDB_EINVAL;
+    if (n == 0) return 0;
+    dropout_kernel<<<ew_grid2(n / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(out), n / 4, p, seed, site);
+    return (int)cudaGetLastError();
+}
+
+// out = round-to-nearest TF32 of x (operands of the tensor-core kernels; tcgen05 truncates otherwise)
+int mdb_round_tf32_f32(const float* x, float* out, long long n, void* stream) {
+    if (!x || !out || n < 0) return MDB_EINVAL;
+    if (n == 0) return 0;
+    round_tf32_kernel<<<ew_grid2(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, n);
+    return (int)cudaGetLastError();
+}
+
+// ResNet stem, forward only: x NCHW [B][3][H][W] -> y NHWC [B][Ho][Wo][64], Ho = (H+6-7)/2+1.
+int mdb_stem_conv7x7_bn_relu_f32(const float* x, const float* w, const float* scale, const float* bias, float* y, int B, int H,
+                                 int W, void* stream_) {
+    if (!x || !w || !scale || !bias || !y || B <= 0 || H <= 0 || W <= 0) return MDB_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+    const int smem = (147 * ST_C + 3 * ST_IH * ST_IW) * (int)sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    dim3 grid((Wo + ST_TW - 1) / ST_TW, (Ho + ST_TH - 1) / ST_TH, B);
+    stem_conv_kernel<<<grid, 256, smem, stream>>>(x, w, scale, bias, y, H, W, Ho, Wo);
+    return (int)cudaGetLastError();
+}
+
+int mdb_maxpool3x3s2_nhwc_f32(const float* x, float* y, int B, int H, int W, int C, void* stream) {
+    if (!x || !y || B <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 4) return MDB_EINVAL;
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const long long n4 = (long long)B * Ho * Wo * C / 4;
+    maxpool3x3s2_kernel<<<ew_grid2(n4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, B, H, W, C, Ho, Wo);
     return (int)cudaGetLastError();
 }
 

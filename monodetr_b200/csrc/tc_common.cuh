@@ -155,6 +155,12 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_m
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+__device__ __forceinline__ float round_tf32(float v) {   // round-to-nearest (ties away) to TF32; tcgen05 itself truncates
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
 __device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }

@@ -1,0 +1,234 @@
+"""Autograd glue over the C-ABI kernels (forward AND backward run on the sm_100a library; there is no
+PyTorch/CPU fallback).  Activations are channels-last: images NHWC, token tensors (B, L, C).
+
+Dropout sites are identified by an integer `site`; masks are regenerated in backward from the device seed
+(kernels.seed_tensor), so nothing but the seed is kept.
+"""
+import torch
+import torch.nn.functional as F
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib, kernels as K, tc
+from .msda import MSDeformAttnFunction
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+# ---- small raw wrappers ---------------------------------------------------------------------------------
+def relu_backward(dy, y, scale=1.0):
+    dy = dy.contiguous()
+    out = torch.empty_like(dy)
+    _lib.check(_lib.lib().mdb_relu_backward_f32(_p(dy), _p(y), _p(out), dy.numel(), float(scale), _s()), "relu_backward")
+    _lib.count(1)
+    return out
+
+
+def dropout_raw(x, p, site):
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().mdb_dropout_f32(_p(x), _p(out), x.numel(), float(p), _p(K.seed_tensor(x.device)), site, _s()), "dropout")
+    _lib.count(1)
+    return out
+
+
+class _Dropout(Function):
+    @staticmethod
+    def forward(ctx, x, p, site):
+        ctx.p, ctx.site = p, site
+        return dropout_raw(x, p, site)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        return dropout_raw(dy, ctx.p, ctx.site), None, None
+
+
+def dropout(x, p, training, site):
+    if not training or p <= 0.0:
+        return x
+    return _Dropout.apply(x, p, site)
+
+
+# ---- linear ----------------------------------------------------------------------------------------------
+class _Linear(Function):
+    """y = act(x W^T + b + residual); W (N, K) as stored by nn.Linear.  N is padded to a multiple of 4 internally."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, residual, relu):
+        K_ = x.shape[-1]
+        N = w.shape[0]
+        Np = _pad4(N)
+        x2 = x.reshape(-1, K_)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        wr = tc.round_tf32(w.contiguous())
+        bp = b
+        if Np != N:
+            wr = F.pad(wr, (0, 0, 0, Np - N))
+            bp = None if b is None else F.pad(b, (0, Np - N))
+        r2 = None
+        if residual is not None:
+            assert Np == N
+            r2 = residual.reshape(-1, N).contiguous()
+        y = tc.linear_forward(x2, wr, None if bp is None else bp.contiguous(), r2, relu=relu)
+        ctx.save_for_backward(x2, wr, y if relu else None)
+        ctx.meta = (x.shape, N, Np, b is not None, residual is not None, relu)
+        out = y if Np == N else y[:, :N].contiguous()
+        return out.view(*x.shape[:-1], N)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, wr, y = ctx.saved_tensors
+        xshape, N, Np, has_b, has_res, relu = ctx.meta
+        dy2 = dy.reshape(-1, N)
+        if Np != N:
+            dy2 = F.pad(dy2, (0, Np - N))
+        dy2 = dy2.contiguous()
+        if relu:
+            dy2 = relu_backward(dy2, y)
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = tc.linear_dgrad(dy2, wr).view(xshape)
+        if ctx.needs_input_grad[1]:
+            dw = tc.linear_wgrad(dy2, x2)
+            if Np != N:
+                dw = dw[:N]
+        if has_b and ctx.needs_input_grad[2]:
+            db = tc.colsum(dy2)
+            if Np != N:
+                db = db[:N]
+        if has_res and ctx.needs_input_grad[3]:
+            dres = dy2.view(*xshape[:-1], N)
+        return dx, dw, db, dres, None
+
+
+def linear(x, w, b=None, residual=None, relu=False):
+    return _Linear.apply(x, w, b, residual, relu)
+
+
+# ---- generic NHWC convolution with bias (neck / depth predictor; the ResNet body has its own schedule) ----
+class _Conv2d(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, stride, pad):
+        O, I, kh, kw = w.shape
+        Op = _pad4(O)
+        wp = tc.pack_weight(w.contiguous())                      # (taps, O, I), rounded to TF32
+        bp = b
+        if Op != O:
+            wp = F.pad(wp, (0, 0, 0, Op - O))
+            bp = None if b is None else F.pad(b, (0, Op - O))
+        y = tc.conv2d_forward(x, wp, None if bp is None else bp.contiguous(), None, kh, kw, stride, pad)
+        ctx.save_for_backward(x, wp)
+        ctx.meta = (O, Op, kh, kw, stride, pad, b is not None)
+        return y if Op == O else y[..., :O].contiguous()
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, wp = ctx.saved_tensors
+        O, Op, kh, kw, stride, pad, has_b = ctx.meta
+        if Op != O:
+            dy = F.pad(dy, (0, Op - O))
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = tc.conv2d_dgrad(dy, wp, x.shape, None, None, kh, kw, stride, pad)
+        if ctx.needs_input_grad[1]:
+            dw = tc.unpack_wgrad(tc.conv2d_wgrad(dy, x, None, kh, kw, stride, pad), kh, kw)
+            if Op != O:
+                dw = dw[:O]
+        if has_b and ctx.needs_input_grad[2]:
+            db = tc.colsum(dy.view(-1, Op))
+            if Op != O:
+                db = db[:O]
+        return dx, dw, db, None, None
+
+
+def conv2d_nhwc(x, w, b=None, stride=1, pad=0):
+    return _Conv2d.apply(x.contiguous(), w, b, stride, pad)
+
+
+# ---- normalisation -----------------------------------------------------------------------------------------
+class _AddLayerNorm(Function):
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, eps, drop_p, site):
+        x = x.contiguous()
+        res = None if res is None else res.contiguous()
+        y, mean, rstd = K.add_layernorm_forward(x, res, gamma, beta, eps, drop_p, site)
+        ctx.save_for_backward(x, res, gamma, mean, rstd)
+        ctx.meta = (drop_p, site)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, res, gamma, mean, rstd = ctx.saved_tensors
+        drop_p, site = ctx.meta
+        dx, dres, dg, db = K.add_layernorm_backward(dy, x, res, gamma, mean, rstd, drop_p, site)
+        return dx, (dres if res is not None else None), dg, db, None, None, None
+
+
+def add_layernorm(x, res, gamma, beta, eps=1e-5, drop_p=0.0, training=False, site=0):
+    """LayerNorm(x + dropout(res)) -- the residual/dropout/norm pattern of every transformer sub-block."""
+    return _AddLayerNorm.apply(x, res, gamma, beta, eps, drop_p if training else 0.0, site)
+
+
+class _GroupNorm(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, G, eps, relu):
+        x = x.contiguous()
+        y, mean, rstd = K.groupnorm_forward(x, gamma, beta, G, eps, relu)
+        ctx.save_for_backward(x, y if relu else None, gamma, mean, rstd)
+        ctx.meta = (G, relu)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, y, gamma, mean, rstd = ctx.saved_tensors
+        G, relu = ctx.meta
+        dx, dg, db = K.groupnorm_backward(dy, x, y, gamma, mean, rstd, G, relu)
+        return dx, dg, db, None, None, None
+
+
+def groupnorm_nhwc(x, gamma, beta, G=32, eps=1e-5, relu=False):
+    return _GroupNorm.apply(x, gamma, beta, G, eps, relu)
+
+
+# ---- attention core -----------------------------------------------------------------------------------------
+class _Attention(Function):
+    @staticmethod
+    def forward(ctx, q, k, v, kpm, drop_p, site):
+        out, lse, kp = K.attention_forward(q, k, v, kpm, drop_p, site)
+        ctx.save_for_backward(q, k, v, kp, out, lse)
+        ctx.meta = (drop_p, site)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        q, k, v, kp, out, lse = ctx.saved_tensors
+        drop_p, site = ctx.meta
+        dq, dk, dv = K.attention_backward(q, k, v, kp, out, lse, dout, drop_p, site)
+        return dq, dk, dv, None, None, None
+
+
+def attention(q, k, v, key_padding_mask=None, drop_p=0.0, training=False, site=0):
+    """softmax(q k^T / sqrt(32)) v per head; q (B, Lq, 256), k/v (B, Lk, 256) (strided views allowed)."""
+    return _Attention.apply(q, k, v, key_padding_mask, drop_p if training else 0.0, site)
+
+
+def msda(value, spatial_shapes, level_start_index, sampling_locations, attention_weights):
+    return MSDeformAttnFunction.apply(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, 64)

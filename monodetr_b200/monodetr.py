@@ -1,0 +1,178 @@
+"""MonoDETR top module -- mirror of lib/models/monodetr/monodetr.py (MonoDETR :28-293, MLP :535-547, build :550-614)
+with identical constructor arguments, parameter names (state_dict keys incl. the decoder aliases :129-131),
+initialisation rules and forward signature / output dict (:150, :270-283), running on the sm_100a kernels.
+
+Only the configs/monodetr.yaml branch is implemented (with_box_refine=True, two_stage=False, use_dab=False,
+two_stage_dino=False, use_dn=False); other branches raise NotImplementedError instead of silently differing.
+"""
+import copy
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import functional as Fn
+from .backbone import build_backbone
+from .depth_predictor import DepthPredictor
+from .depthaware_transformer import MLP, build_depthaware_transformer, inverse_sigmoid
+
+
+def _get_clones(module, N):
+    return nn.ModuleList([copy.deepcopy(module) for _ in range(N)])
+
+
+class _ProjGN(nn.Sequential):
+    """input_proj entry: Sequential(Conv2d, GroupNorm(32, hidden)) (reference :83-91) with an NHWC forward."""
+
+    def forward(self, x):
+        conv, gn = self[0], self[1]
+        y = Fn.conv2d_nhwc(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0])
+        return Fn.groupnorm_nhwc(y, gn.weight, gn.bias, gn.num_groups, gn.eps, False)
+
+
+def bilinear_sample_align_corners(depth, xy):
+    """F.grid_sample(depth[:, None], xy[:, :, None], bilinear, zeros, align_corners=True) (reference :248-253) written
+    with gathers so it never dispatches to cuDNN's grid sampler.  depth (B, H, W), xy (B, N, 2) in [-1, 1] -> (B, N)."""
+    B, H, W = depth.shape
+    x = (xy[..., 0] + 1) * 0.5 * (W - 1)
+    y = (xy[..., 1] + 1) * 0.5 * (H - 1)
+    x0 = x.floor()
+    y0 = y.floor()
+    lx, ly = x - x0, y - y0
+    flat = depth.reshape(B, H * W)
+
+    def tap(yy, xx):
+        ok = (xx >= 0) & (xx <= W - 1) & (yy >= 0) & (yy <= H - 1)
+        idx = (yy.clamp(0, H - 1) * W + xx.clamp(0, W - 1)).long()
+        return torch.gather(flat, 1, idx) * ok.to(depth.dtype)
+    return (tap(y0, x0) * (1 - ly) * (1 - lx) + tap(y0, x0 + 1) * (1 - ly) * lx
+            + tap(y0 + 1, x0) * ly * (1 - lx) + tap(y0 + 1, x0 + 1) * ly * lx)
+
+
+class MonoDETR(nn.Module):
+    """Monocular 3D detector; same constructor as the reference (:30-31)."""
+
+    def __init__(self, backbone, depthaware_transformer, depth_predictor, num_classes, num_queries, num_feature_levels,
+                 aux_loss=True, with_box_refine=False, two_stage=False, init_box=False, use_dab=False, group_num=11,
+                 two_stage_dino=False):
+        super().__init__()
+        if two_stage or use_dab or two_stage_dino or not with_box_refine or num_feature_levels != 4:
+            raise NotImplementedError("monodetr_b200 implements the configs/monodetr.yaml model branch only")
+        self.num_queries = num_queries
+        self.depthaware_transformer = depthaware_transformer
+        self.depth_predictor = depth_predictor
+        hidden_dim = depthaware_transformer.d_model
+        self.hidden_dim = hidden_dim
+        self.num_feature_levels = num_feature_levels
+        self.two_stage_dino = two_stage_dino
+        self.label_enc = nn.Embedding(num_classes + 1, hidden_dim - 1)
+        self.class_embed = nn.Linear(hidden_dim, num_classes)
+        prior_prob = 0.01
+        bias_value = -math.log((1 - prior_prob) / prior_prob)
+        self.class_embed.bias.data = torch.ones(num_classes) * bias_value
+        self.bbox_embed = MLP(hidden_dim, hidden_dim, 6, 3)
+        self.dim_embed_3d = MLP(hidden_dim, hidden_dim, 3, 2)
+        self.angle_embed = MLP(hidden_dim, hidden_dim, 24, 2)
+        self.depth_embed = MLP(hidden_dim, hidden_dim, 2, 2)
+        self.use_dab = use_dab
+        if init_box:
+            nn.init.constant_(self.bbox_embed.layers[-1].weight.data, 0)
+            nn.init.constant_(self.bbox_embed.layers[-1].bias.data, 0)
+        self.query_embed = nn.Embedding(num_queries * group_num, hidden_dim * 2)
+        input_proj_list = []
+        for i in range(len(backbone.strides)):
+            in_channels = backbone.num_channels[i]
+            input_proj_list.append(_ProjGN(nn.Conv2d(in_channels, hidden_dim, kernel_size=1), nn.GroupNorm(32, hidden_dim)))
+        for _ in range(num_feature_levels - len(backbone.strides)):
+            input_proj_list.append(_ProjGN(nn.Conv2d(in_channels, hidden_dim, kernel_size=3, stride=2, padding=1),
+                                           nn.GroupNorm(32, hidden_dim)))
+            in_channels = hidden_dim
+        self.input_proj = nn.ModuleList(input_proj_list)
+        self.backbone = backbone
+        self.aux_loss = aux_loss
+        self.with_box_refine = with_box_refine
+        self.two_stage = two_stage
+        self.num_classes = num_classes
+        for proj in self.input_proj:
+            nn.init.xavier_uniform_(proj[0].weight, gain=1)
+            nn.init.constant_(proj[0].bias, 0)
+        num_pred = depthaware_transformer.decoder.num_layers
+        self.class_embed = _get_clones(self.class_embed, num_pred)
+        self.bbox_embed = _get_clones(self.bbox_embed, num_pred)
+        nn.init.constant_(self.bbox_embed[0].layers[-1].bias.data[2:], -2.0)
+        self.depthaware_transformer.decoder.bbox_embed = self.bbox_embed          # alias keys (:129-131)
+        self.dim_embed_3d = _get_clones(self.dim_embed_3d, num_pred)
+        self.depthaware_transformer.decoder.dim_embed = self.dim_embed_3d
+        self.angle_embed = _get_clones(self.angle_embed, num_pred)
+        self.depth_embed = _get_clones(self.depth_embed, num_pred)
+
+    def forward(self, images, calibs, targets, img_sizes, dn_args=None):
+        """images (B, 3, H, W) fp32 NCHW; calibs (B, 3, 4); targets / dn_args ignored; img_sizes (B, 2) [W, H]."""
+        features, pos = self.backbone(images)                                      # NHWC maps, (HW, C) tables
+        srcs = [self.input_proj[l](feat) for l, feat in enumerate(features)]
+        for l in range(len(srcs), self.num_feature_levels):
+            src = self.input_proj[l](features[-1] if l == len(features) else srcs[-1])
+            srcs.append(src)
+            pos.append(self.backbone[1](src))
+        query_embeds = self.query_embed.weight if self.training else self.query_embed.weight[:self.num_queries]
+
+        depth_logits, depth_pos_embed, weighted_depth, depth_pos_embed_ip = self.depth_predictor(srcs, None, pos[1])
+        hs, init_reference, inter_references, inter_references_dim, boxes = self.depthaware_transformer(
+            srcs, None, pos, query_embeds, depth_pos_embed, depth_pos_embed_ip)
+
+        outputs_coords, outputs_classes, outputs_3d_dims, outputs_depths, outputs_angles = [], [], [], [], []
+        for lvl in range(hs.shape[0]):
+            # The reference re-evaluates bbox_embed[lvl](hs[lvl]) + inverse_sigmoid(reference) here (:216-228); that is the
+            # very tensor the decoder already formed before detaching it, so it is reused (same values, same gradients).
+            outputs_coord = boxes[lvl]
+            outputs_coords.append(outputs_coord)
+            cls = self.class_embed[lvl]
+            outputs_classes.append(Fn.linear(hs[lvl], cls.weight, cls.bias))
+            size3d = inter_references_dim[lvl]
+            outputs_3d_dims.append(size3d)
+            box2d_height_norm = outputs_coord[:, :, 4] + outputs_coord[:, :, 5]
+            box2d_height = torch.clamp(box2d_height_norm * img_sizes[:, 1:2], min=1.0)
+            depth_geo = size3d[:, :, 0] / box2d_height * calibs[:, 0, 0].unsqueeze(1)
+            depth_reg = self.depth_embed[lvl](hs[lvl])
+            outputs_center3d = ((outputs_coord[..., :2] - 0.5) * 2).detach()
+            depth_map = bilinear_sample_align_corners(weighted_depth, outputs_center3d).unsqueeze(-1)
+            depth_ave = torch.cat([((1. / (depth_reg[:, :, 0:1].sigmoid() + 1e-6) - 1.) + depth_geo.unsqueeze(-1) + depth_map) / 3,
+                                   depth_reg[:, :, 1:2]], -1)
+            outputs_depths.append(depth_ave)
+            outputs_angles.append(self.angle_embed[lvl](hs[lvl]))
+
+        out = {"pred_logits": outputs_classes[-1], "pred_boxes": outputs_coords[-1], "pred_3d_dim": outputs_3d_dims[-1],
+               "pred_depth": outputs_depths[-1], "pred_angle": outputs_angles[-1],
+               "pred_depth_map_logits": depth_logits.permute(0, 3, 1, 2)}          # (B, 81, H, W) view of the NHWC logits
+        if self.aux_loss:
+            out["aux_outputs"] = [{"pred_logits": a, "pred_boxes": b, "pred_3d_dim": c, "pred_angle": d, "pred_depth": e}
+                                  for a, b, c, d, e in zip(outputs_classes[:-1], outputs_coords[:-1], outputs_3d_dims[:-1],
+                                                           outputs_angles[:-1], outputs_depths[:-1])]
+        return out
+
+
+def build(cfg, criterion_builder=None):
+    """Same contract as the reference's build(cfg) (:550-614): returns (model, criterion).  The criterion
+    (SetCriterion + HungarianMatcher) is outside the hot path: pass `criterion_builder(cfg)` -- e.g. the
+    reference's own -- or get None."""
+    backbone = build_backbone(cfg)
+    depthaware_transformer = build_depthaware_transformer(cfg)
+    depth_predictor = DepthPredictor(cfg)
+    model = MonoDETR(backbone, depthaware_transformer, depth_predictor, num_classes=cfg["num_classes"],
+                     num_queries=cfg["num_queries"], aux_loss=cfg["aux_loss"], num_feature_levels=cfg["num_feature_levels"],
+                     with_box_refine=cfg["with_box_refine"], two_stage=cfg["two_stage"], init_box=cfg["init_box"],
+                     use_dab=cfg["use_dab"], two_stage_dino=cfg["two_stage_dino"])
+    criterion = criterion_builder(cfg) if criterion_builder is not None else None
+    return model, criterion
+
+
+DEFAULT_MODEL_CFG = {
+    # configs/monodetr.yaml `model:` section (the keys the builders read)
+    "num_classes": 3, "return_intermediate_dec": True, "device": "cuda", "backbone": "resnet50", "train_backbone": True,
+    "num_feature_levels": 4, "dilation": False, "position_embedding": "sine", "masks": False, "mode": "LID",
+    "num_depth_bins": 80, "depth_min": 1e-3, "depth_max": 60.0, "with_box_refine": True, "two_stage": False,
+    "use_dab": False, "use_dn": False, "two_stage_dino": False, "init_box": False, "enc_layers": 3, "dec_layers": 3,
+    "hidden_dim": 256, "dim_feedforward": 256, "dropout": 0.1, "nheads": 8, "num_queries": 50, "enc_n_points": 4,
+    "dec_n_points": 4, "aux_loss": True,
+}

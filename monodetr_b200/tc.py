@@ -57,7 +57,7 @@ def colsum(x2d):
     return out
 
 
-def conv2d_forward(x, w_packed, bias=None, residual=None, kh=1, kw=1, stride=1, pad=0, relu=False):
+def conv2d_forward(x, w_packed, bias=None, residual=None, kh=1, kw=1, stride=1, pad=0, relu=False, round_out=False):
     _chk(x, w_packed, bias, residual)
     B, H, W, Cin = x.shape
     taps, Cout, Cin2 = w_packed.shape
@@ -67,20 +67,20 @@ def conv2d_forward(x, w_packed, bias=None, residual=None, kh=1, kw=1, stride=1, 
     if residual is not None:
         assert residual.shape == y.shape
     rc = _lib.lib().mdb_conv2d_forward_f32(_p(x), _p(w_packed), _p(bias), _p(residual), _p(y), B, H, W, Cin, Cout, kh, kw,
-                                           stride, pad, int(relu), _s())
+                                           stride, pad, int(relu) | (int(round_out) << 1), _s())
     _lib.check(rc, "conv2d_forward")
     _lib.count(1)
     return y
 
 
-def conv2d_dgrad(dy, w_packed, x_shape, residual=None, relu_mask=None, kh=1, kw=1, stride=1, pad=0):
+def conv2d_dgrad(dy, w_packed, x_shape, residual=None, relu_mask=None, kh=1, kw=1, stride=1, pad=0, round_out=False):
     _chk(dy, w_packed, residual, relu_mask)
     B, H, W, Cin = x_shape
     taps, Cout, Cin2 = w_packed.shape
     assert Cin2 == Cin and dy.shape[-1] == Cout
     dx = torch.empty((B, H, W, Cin), dtype=torch.float32, device=dy.device)
     rc = _lib.lib().mdb_conv2d_dgrad_f32(_p(dy), _p(w_packed), _p(residual), _p(relu_mask), _p(dx), B, H, W, Cin, Cout, kh,
-                                         kw, stride, pad, _s())
+                                         kw, stride, pad, int(round_out) << 1, _s())
     _lib.check(rc, "conv2d_dgrad")
     _lib.count(stride * stride)
     return dx
@@ -99,11 +99,20 @@ def conv2d_wgrad(dy, x, rowscale=None, kh=1, kw=1, stride=1, pad=0):
 
 
 # ---- linear layers = 1x1 convolution over a 1-row "image" of M pixels ---------------------------------
-def linear_forward(x2d, w, bias=None, residual=None, relu=False):
+def round_tf32(x):
+    """Round-to-nearest TF32 copy of x (weights of linear layers before they become tensor-core operands)."""
+    _chk(x)
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().mdb_round_tf32_f32(_p(x), _p(out), x.numel(), _s()), "round_tf32")
+    _lib.count(1)
+    return out
+
+
+def linear_forward(x2d, w, bias=None, residual=None, relu=False, round_out=False):
     M, K = x2d.shape
     N = w.shape[0]
     y = conv2d_forward(x2d.view(1, 1, M, K), w.view(1, N, K), bias, None if residual is None else residual.view(1, 1, M, N),
-                       relu=relu)
+                       relu=relu, round_out=round_out)
     return y.view(M, N)
 
 

@@ -90,7 +90,7 @@ def test_conv_forward_backward(cfg):
     x_nhwc = x.permute(0, 2, 3, 1).contiguous()
     wp = tc.pack_weight(w, scale)
     ref_wp = (w * scale.view(-1, 1, 1, 1)).permute(2, 3, 0, 1).reshape(k * k, Cout, Cin)
-    assert torch.equal(wp, ref_wp.contiguous())
+    assert _relerr(wp, ref_wp.contiguous()) < 6e-4          # packed weights are rounded to TF32 (round-to-nearest)
     ws = w * scale.view(-1, 1, 1, 1)
     ref = F.conv2d(x, ws, bias, stride=s, padding=pad)
     res = torch.randn_like(ref)
