@@ -69,6 +69,10 @@ int mdb_msda_backward_f64(const double* value, const int64_t* spatial_shapes, co
  * with B=1, H=1, W=M, Cin=K, Cout=N, kh=kw=1, stride=1, pad=0 (w itself is already "packed").
  * Supported: kh=kw in {1,3}, stride in {1,2}, Cin%4==0, Cout%4==0, 16-byte aligned pointers.
  */
+/* Arithmetic of the tensor-core family: 1 (default) = error-compensated 3xTF32 (A*B + A_lo*B + A*B_lo, ~fp32 accuracy,
+ * what the 1e-3 parity tests run); 0 = single-pass TF32 with round-to-nearest operands (cuDNN's allow_tf32 class). */
+int mdb_set_precision(int mode);
+int mdb_get_precision(void);
 int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* bias /*[Cout]|NULL*/,
                            const float* residual /*like y|NULL*/, float* y,
                            int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
@@ -81,7 +85,8 @@ int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* re
 int mdb_conv2d_wgrad_f32(const float* dy, const float* x, const float* rowscale /*[Cout]|NULL*/, float* dw_packed,
                          int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
                          int accumulate, void* stream);
-/* w_packed[t][o][i] = rn_tf32( w_oihw[o][i][t] * (scale ? scale[o] : 1) )   (FrozenBatchNorm fold, backbone.py:54-64) */
+/* w_packed[t][o][i] = w_oihw[o][i][t] * (scale ? scale[o] : 1), rounded to nearest TF32 in precision mode 0
+ * (FrozenBatchNorm fold, backbone.py:54-64) */
 int mdb_pack_conv_weight_f32(const float* w_oihw, const float* scale, float* w_packed, int O, int I, int taps,
                              void* stream);
 int mdb_unpack_conv_wgrad_f32(const float* dw_packed, float* dw_oihw, int O, int I, int taps, int accumulate,

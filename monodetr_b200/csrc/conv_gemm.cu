@@ -56,20 +56,25 @@ struct TcParams {
     float* out;
 };
 
-template <int BN, int STAGES, int MODE /*0 fprop/dgrad, 1 wgrad*/, bool B_MN>
+// SPLIT = error-compensated "3xTF32": the four epilogue warps double as splitter warps during the main loop; for
+// every landed stage they write lo = x - trunc_tf32(x) of both tiles next to the raw tiles, and the MMA warp issues
+// A*B + A_lo*B + A*B_lo (the tensor core truncates the raw fp32 bits itself), which restores ~fp32 accuracy.
+template <int BN, int STAGES, int MODE /*0 fprop/dgrad, 1 wgrad*/, bool B_MN, bool SPLIT>
 __global__ void __launch_bounds__(kThreadsTC)
 tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const __grid_constant__ TcParams p) {
     constexpr bool A_MN = (MODE == 1);
     constexpr int kTileBBytes = BN * 128;
-    constexpr int kStageBytes = kTileABytes + kTileBBytes;
+    constexpr int kRawBytes = kTileABytes + kTileBBytes;          // what TMA delivers per stage
+    constexpr int kStageBytes = SPLIT ? 2 * kRawBytes : kRawBytes;  // + the lo tiles
     static_assert(!(MODE == 1) || B_MN, "wgrad reads both operands MN-major");
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full = empty_bar + STAGES;
+    uint64_t* split_bar = empty_bar + STAGES;                     // splitter warps -> MMA (SPLIT only)
+    uint64_t* tmem_full = split_bar + STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5;
@@ -100,6 +105,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
+            mbar_init(&split_bar[s], 4);                          // one arrival per splitter warp
         }
         mbar_init(tmem_full, 1);
         fence_mbar_init();
@@ -119,7 +125,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* a_dst = smem + s * kStageBytes;
                 uint8_t* b_dst = a_dst + kTileABytes;
-                mbar_arrive_expect_tx(&full_bar[s], kStageBytes);
+                mbar_arrive_expect_tx(&full_bar[s], kRawBytes);
                 if constexpr (MODE == 0) {
                     const int tap = it / p.cblocks;
                     const int cb = it - tap * p.cblocks;
@@ -156,7 +162,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             for (int it = 0; it < total_iters; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+                mbar_wait(SPLIT ? &split_bar[s] : &full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
                 const uint32_t b_addr = a_addr + kTileABytes;
@@ -165,18 +171,48 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     // K-major (SWIZZLE_128B): 8 fp32 = 32 B further along the 128-B row; 8-row groups 1024 B apart (SBO).
                     // MN-major (128B swizzle, 32-B atoms, 4-row period): 8 reduction rows = 1024 B further per k-step;
                     // 4-row groups 512 B apart (SBO); 32-wide MN chunks 4096 B apart (LBO).
-                    const uint64_t adesc = A_MN ? make_smem_desc(a_addr + k * 1024, kChunkBytes, 512, 1)
-                                                : make_smem_desc(a_addr + k * 32, 16, 1024, 2);
-                    const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * 1024, kChunkBytes, 512, 1)
-                                                : make_smem_desc(b_addr + k * 32, 16, 1024, 2);
+                    const uint32_t ao = A_MN ? k * 1024 : k * 32, bo = B_MN ? k * 1024 : k * 32;
+                    const uint64_t adesc = A_MN ? make_smem_desc(a_addr + ao, kChunkBytes, 512, 1) : make_smem_desc(a_addr + ao, 16, 1024, 2);
+                    const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + bo, kChunkBytes, 512, 1) : make_smem_desc(b_addr + bo, 16, 1024, 2);
                     umma_tf32(tmem_base, adesc, bdesc, idesc, (it > 0) || (k > 0));
+                    if constexpr (SPLIT) {
+                        const uint64_t alo = A_MN ? make_smem_desc(a_addr + kRawBytes + ao, kChunkBytes, 512, 1)
+                                                  : make_smem_desc(a_addr + kRawBytes + ao, 16, 1024, 2);
+                        const uint64_t blo = B_MN ? make_smem_desc(b_addr + kRawBytes + bo, kChunkBytes, 512, 1)
+                                                  : make_smem_desc(b_addr + kRawBytes + bo, 16, 1024, 2);
+                        umma_tf32(tmem_base, alo, bdesc, idesc, true);
+                        umma_tf32(tmem_base, adesc, blo, idesc, true);
+                    }
                 }
                 umma_commit(&empty_bar[s]);    // frees the smem stage when these MMAs retire
             }
             umma_commit(tmem_full);            // accumulator complete
         }
     } else {
-        // ================================ epilogue =================================================
+        // ================================ splitter (SPLIT) + epilogue ================================
+        if constexpr (SPLIT) {
+            const int t = threadIdx.x - 64;    // 0..127
+            for (int it = 0; it < total_iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                const uint4* raw = reinterpret_cast<const uint4*>(smem + s * kStageBytes);
+                float4* lo = reinterpret_cast<float4*>(smem + s * kStageBytes + kRawBytes);
+#pragma unroll 4
+                for (int i = t; i < kRawBytes / 16; i += 128) {
+                    const uint4 r = raw[i];
+                    float4 l;
+                    l.x = __uint_as_float(r.x) - __uint_as_float(r.x & 0xFFFFE000u);
+                    l.y = __uint_as_float(r.y) - __uint_as_float(r.y & 0xFFFFE000u);
+                    l.z = __uint_as_float(r.z) - __uint_as_float(r.z & 0xFFFFE000u);
+                    l.w = __uint_as_float(r.w) - __uint_as_float(r.w & 0xFFFFE000u);
+                    lo[i] = l;
+                }
+                fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&split_bar[s]);
+            }
+        }
         const int q = warp & 3;                // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
         bool row_ok;
@@ -309,11 +345,13 @@ int make_map(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, 
     return r == CUDA_SUCCESS ? 0 : MDB_EINVAL;
 }
 
-template <int BN, int STAGES, int MODE, bool B_MN>
+int g_precision = 1;   // 0 = single-pass TF32 (operands rounded to nearest), 1 = error-compensated 3xTF32 (default)
+
+template <int BN, int STAGES, int MODE, bool B_MN, bool SPLIT>
 int launch_tc(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t stream) {
-    constexpr int smem = STAGES * (kTileABytes + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
+    constexpr int smem = STAGES * (SPLIT ? 2 : 1) * (kTileABytes + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
     static bool configured = false;
-    auto kern = tc_conv_gemm_kernel<BN, STAGES, MODE, B_MN>;
+    auto kern = tc_conv_gemm_kernel<BN, STAGES, MODE, B_MN, SPLIT>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
@@ -351,6 +389,13 @@ int check_geom(const ConvGeom& g) {
 
 extern "C" {
 
+int mdb_set_precision(int mode) {
+    if (mode != 0 && mode != 1) return MDB_EINVAL;
+    g_precision = mode;
+    return 0;
+}
+int mdb_get_precision(void) { return g_precision; }
+
 // y[B,Ho,Wo,Cout] = act( conv(x[B,H,W,Cin], w_packed[kh*kw][Cout][Cin]) + bias + residual )
 int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
                            int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int flags,
@@ -375,7 +420,7 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
             const int t = ky * kw + kx;
             p.tap_dy[t] = ky - pad; p.tap_dx[t] = kx - pad; p.tap_w[t] = t;
         }
-    p.No = Cout; p.ldo = Cout; p.relu = flags & 1; p.round_out = (flags >> 1) & 1; p.atomic_out = 0;
+    p.No = Cout; p.ldo = Cout; p.relu = flags & 1; p.round_out = (g_precision == 0) ? ((flags >> 1) & 1) : 0; p.atomic_out = 0;
     p.bias = bias; p.residual = residual; p.relu_mask = nullptr; p.rowscale = nullptr; p.out = y;
 
     CUtensorMap ma, mb;
@@ -388,7 +433,7 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
         rc = make_map(&ma, x, 4, dims, str, box, es);
         if (rc) return rc;
     }
-    const bool wide = (Cout >= 256) && ((long long)B * p.tiles_x * p.tiles_y * (Cout / 256) >= 120);
+    const bool wide = (g_precision == 0) && (Cout >= 256) && ((long long)B * p.tiles_x * p.tiles_y * (Cout / 256) >= 120);
     const int bn = wide ? 256 : 128;
     {   // B: packed weights as (Cin, Cout, taps), box (32, BN, 1)
         uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
@@ -398,8 +443,9 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
         if (rc) return rc;
     }
     dim3 grid((Cout + bn - 1) / bn, B * p.tiles_x * p.tiles_y, 1);
-    if (wide) return launch_tc<256, 4, 0, false>(ma, mb, p, grid, stream);
-    return launch_tc<128, 3, 0, false>(ma, mb, p, grid, stream);
+    if (g_precision == 1) return launch_tc<128, 3, 0, false, true>(ma, mb, p, grid, stream);
+    if (wide) return launch_tc<256, 4, 0, false, false>(ma, mb, p, grid, stream);
+    return launch_tc<128, 3, 0, false, false>(ma, mb, p, grid, stream);
 }
 
 // dx[B,H,W,Cin] = (conv_transpose(dy[B,Ho,Wo,Cout], w_packed) + residual) * (relu_mask > 0)
@@ -440,7 +486,7 @@ int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* re
                 }
             }
             p.ntaps = nt;
-            p.No = Cin; p.ldo = Cin; p.relu = 0; p.atomic_out = 0; p.round_out = (flags >> 1) & 1;
+            p.No = Cin; p.ldo = Cin; p.relu = 0; p.atomic_out = 0; p.round_out = (g_precision == 0) ? ((flags >> 1) & 1) : 0;
             p.bias = nullptr; p.residual = residual; p.relu_mask = relu_mask; p.rowscale = nullptr; p.out = dx;
             CUtensorMap ma, mb;
             {   // A: dy as (Cout, Wo, Ho, B), unit stride
@@ -461,7 +507,8 @@ int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* re
             if (nt == 0) {   // no tap reaches this parity class (1x1 stride 2): result = (0 + residual) * mask
                 p.ntaps = 0;
             }
-            rc = launch_tc<128, 3, 0, true>(ma, mb, p, grid, stream);
+            rc = (g_precision == 1) ? launch_tc<128, 3, 0, true, true>(ma, mb, p, grid, stream)
+                                    : launch_tc<128, 3, 0, true, false>(ma, mb, p, grid, stream);
             if (rc) return rc;
         }
     return 0;
@@ -488,7 +535,7 @@ int mdb_conv2d_wgrad_f32(const float* dy, const float* x, const float* rowscale,
     p.rtiles_y = (g.Ho + p.rth - 1) / p.rth;
     p.n_img = B;
     const int total_red = B * p.rtiles_x * p.rtiles_y;
-    const int bn = (Cin >= 256) ? 256 : 128;
+    const int bn = (g_precision == 0 && Cin >= 256) ? 256 : 128;
     const int tiles = ((Cout + BM - 1) / BM) * ((Cin + bn - 1) / bn) * taps;
     int splits = (296 + tiles - 1) / tiles;            // aim at ~2 waves of 148 SMs
     if (splits > total_red) splits = total_red;
@@ -520,8 +567,9 @@ int mdb_conv2d_wgrad_f32(const float* dy, const float* x, const float* rowscale,
         p.w_dx = t % kw - pad;
         p.out = dw_packed + (size_t)t * Cout * Cin;
         dim3 grid((Cin + bn - 1) / bn, (Cout + BM - 1) / BM, splits);
-        rc = (bn == 256) ? launch_tc<256, 4, 1, true>(ma, mb, p, grid, stream)
-                         : launch_tc<128, 3, 1, true>(ma, mb, p, grid, stream);
+        rc = (g_precision == 1) ? launch_tc<128, 3, 1, true, true>(ma, mb, p, grid, stream)
+             : (bn == 256)      ? launch_tc<256, 4, 1, true, false>(ma, mb, p, grid, stream)
+                                : launch_tc<128, 3, 1, true, false>(ma, mb, p, grid, stream);
         if (rc) return rc;
     }
     return 0;

@@ -9,7 +9,7 @@
 namespace {
 
 __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale, float* __restrict__ out,
-                                   int O, int I, int taps) {
+                                   int O, int I, int taps, int round_tf32_out) {
     const long long n = (long long)O * I * taps;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         // i indexes the OUTPUT [tap][o][ci] so writes are coalesced
@@ -19,9 +19,12 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
         const int t = (int)(r / O);
         float v = w[((size_t)o * I + ci) * taps + t];
         if (scale) v *= scale[o];
-        uint32_t rb;   // round-to-nearest TF32: the packed weights are tensor-core operands (tcgen05 truncates)
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rb) : "f"(v));
-        out[i] = __uint_as_float(rb);
+        if (round_tf32_out) {   // single-pass TF32 mode: round-to-nearest (tcgen05 would truncate)
+            uint32_t rb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rb) : "f"(v));
+            v = __uint_as_float(rb);
+        }
+        out[i] = v;
     }
 }
 
@@ -63,12 +66,15 @@ __global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ o
 
 extern "C" {
 
+int mdb_get_precision(void);
+
 int mdb_pack_conv_weight_f32(const float* w_oihw, const float* scale, float* w_packed, int O, int I, int taps,
                              void* stream) {
     if (!w_oihw || !w_packed || O <= 0 || I <= 0 || taps <= 0) return MDB_EINVAL;
     const long long n = (long long)O * I * taps;
     const int grid = (int)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
-    pack_weight_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w_oihw, scale, w_packed, O, I, taps);
+    pack_weight_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(w_oihw, scale, w_packed, O, I, taps,
+                                                                             mdb_get_precision() == 0);
     return (int)cudaGetLastError();
 }
 

@@ -99,9 +99,21 @@ def conv2d_wgrad(dy, x, rowscale=None, kh=1, kw=1, stride=1, pad=0):
 
 
 # ---- linear layers = 1x1 convolution over a 1-row "image" of M pixels ---------------------------------
+def set_precision(mode: str):
+    """'tf32x3' (default; error-compensated, ~fp32 accuracy) or 'tf32' (single pass, operands rounded to nearest)."""
+    _lib.check(_lib.lib().mdb_set_precision({"tf32": 0, "tf32x3": 1}[mode]), "set_precision")
+
+
+def get_precision() -> str:
+    return ("tf32", "tf32x3")[_lib.lib().mdb_get_precision()]
+
+
 def round_tf32(x):
-    """Round-to-nearest TF32 copy of x (weights of linear layers before they become tensor-core operands)."""
+    """Round-to-nearest TF32 copy of x (weights of linear layers before they become tensor-core operands);
+    identity in the default 'tf32x3' mode, where operands keep all fp32 bits."""
     _chk(x)
+    if _lib.lib().mdb_get_precision() == 1:
+        return x
     out = torch.empty_like(x)
     _lib.check(_lib.lib().mdb_round_tf32_f32(_p(x), _p(out), x.numel(), _s()), "round_tf32")
     _lib.count(1)
