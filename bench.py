@@ -279,6 +279,16 @@ def cpu_baseline_msda(Lq, budget_s=12.0, threads=None):
             "sample": f"msda core fwd+bwd (grid_sample port of ms_deform_attn_core_pytorch), B={Bs}, Lq={Lq}, {n} passes"}
 
 
+def cpu_baseline_model():
+    """CPU port of the reference model path (oracle/monodetr_torch.py), train shapes, fwd+bwd, bounded sample."""
+    from oracle import monodetr_torch as om
+
+    class A:
+        steps, warmup = 2, 1
+    val, dt, sample, threads, cfg = om.bench_reference_model(A)
+    return {"value": val, "unit": "images/sec", "cores": threads, "kind": "port", "sample": sample + f", {A.steps} timed steps"}
+
+
 # ------------------------------------------------------------------------------------------------
 # reference arm (CPU)
 # ------------------------------------------------------------------------------------------------
@@ -321,7 +331,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("MDB_BENCH_WORKLOAD", "msda"), choices=["model", "msda"])
+    ap.add_argument("--workload", default=os.environ.get("MDB_BENCH_WORKLOAD", "model"), choices=["model", "msda"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 8 at N=1, 16 at N>1 for model)")
     ap.add_argument("--lq", type=int, default=10200)
     ap.add_argument("--uniform-loc", action="store_true")
@@ -347,6 +357,8 @@ def main():
     else:
         from monodetr_b200 import bench_model
         line = bench_model.run(args, rank, local_rank, ws)
+        if line is not None and ws == 1:
+            line["cpu_baseline"] = cpu_baseline_model()
     if line is not None:
         print(json.dumps(line), flush=True)
     if ws > 1:

@@ -1,0 +1,218 @@
+"""bench.py --workload model: full MonoDETR forward+backward (train mode: 550 queries, group self-attention, dropout
+0.1), ResNet-50, 1280x384 synthetic images, surrogate loss sum_k mean(out_k^2), one flat-bucket NCCL
+all-reduce of the gradients per step when world_size > 1.  The step is captured once in a CUDA graph (fwd + loss +
+bwd; the all-reduce is launched right after the replay on the same stream) so the timed region is GPU-bound.
+"""
+import json
+import os
+import statistics
+import time
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, kernels as K, tc
+from . import build_monodetr
+from .ddp import FlatGradBucket, broadcast_parameters
+from .monodetr import DEFAULT_MODEL_CFG
+
+METRIC = "images/sec (1280x384, fwd+bwd)"
+TRAIN_FLOPS_PER_IMAGE = 363.5e9          # matmul+conv fwd+bwd, SURVEY.md 8d
+FULL_S = 10200
+
+
+def surrogate_loss(out):
+    loss = 0.0
+    for k, v in out.items():
+        if k == "aux_outputs":
+            for aux in v:
+                for t in aux.values():
+                    loss = loss + (t ** 2).mean()
+        else:
+            loss = loss + (v ** 2).mean()
+    return loss
+
+
+def synthetic_batch(B, seed):
+    g = torch.Generator().manual_seed(seed)
+    images = torch.randn(B, 3, 384, 1280, generator=g)
+    calibs = torch.zeros(B, 3, 4)
+    calibs[:, 0, 0] = calibs[:, 1, 1] = 721.5377
+    calibs[:, 0, 2] = 609.5593; calibs[:, 1, 2] = 172.854; calibs[:, 0, 3] = 44.85728
+    sizes = torch.tensor([[1242., 375.]]).repeat(B, 1)
+    return images, calibs, sizes
+
+
+class MsdaProbe:
+    """CUDA-event timing of the MSDeformAttn forward launches issued through monodetr_b200.msda (eager steps only)."""
+
+    def __init__(self):
+        self.events = []
+
+    def __enter__(self):
+        from . import msda as _m
+        self._m = _m
+        self._orig = _m.ms_deform_attn_forward
+        probe = self
+
+        def timed(value, shapes, lsi, loc, attn, step):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = probe._orig(value, shapes, lsi, loc, attn, step)
+            e1.record()
+            probe.events.append((e0, e1, value.shape[0], loc.shape[1]))
+            return out
+        _m.ms_deform_attn_forward = timed
+        return self
+
+    def __exit__(self, *a):
+        self._m.ms_deform_attn_forward = self._orig
+
+    def encoder_ms(self):
+        ts = [e0.elapsed_time(e1) for e0, e1, _, lq in self.events if lq == FULL_S]
+        return statistics.mean(ts) if ts else None
+
+
+def run(args, rank, local_rank, ws):
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    B = args.batch or (8 if ws == 1 else 16)
+    precision = os.environ.get("MDB_PRECISION", "tf32x3")
+    tc.set_precision(precision)
+    torch.manual_seed(0)
+    model, _ = build_monodetr(DEFAULT_MODEL_CFG)
+    model = model.to(dev).train()
+    broadcast_parameters(model)
+    bucket = FlatGradBucket(model)
+
+    host = [t.pin_memory() for t in synthetic_batch(B, seed=1000 + rank)]
+    images, calibs, sizes = (t.to(dev) for t in host)
+    loss_buf = torch.zeros((), device=dev)
+    loss_host = torch.zeros(()).pin_memory()
+
+    def fwd_bwd():
+        bucket.zero()
+        K.advance_seed(dev)
+        out = model(images, calibs, None, sizes)
+        loss = surrogate_loss(out)
+        loss.backward()
+        loss_buf.copy_(loss.detach())
+
+    def barrier():
+        if ws > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (eager) then capture --------------------------------------------------------------------
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            fwd_bwd()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    lc0 = _lib.launch_count()
+    graph = None
+    use_graph = os.environ.get("MDB_NO_GRAPH", "0") != "1"
+    if use_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                fwd_bwd()
+        except Exception as e:          # capture is an optimisation of launch overhead only: same kernels either way
+            if rank == 0:
+                print(f"[bench_model] CUDA graph capture failed ({type(e).__name__}: {e}); running eager", flush=True)
+            graph = None
+            torch.cuda.synchronize()
+            lc0 = _lib.launch_count()
+            fwd_bwd()
+    else:
+        fwd_bwd()
+    launches_per_step = _lib.launch_count() - lc0
+
+    def step():
+        if graph is not None:
+            graph.replay()
+        else:
+            fwd_bwd()
+        bucket.all_reduce()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    from bench import ClockSampler, peaks, msda_bytes          # bench.py is the entry script (already imported)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.zero_()
+        evs[i][0].record()
+        step()
+        evs[i][1].record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if ws > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt.item())
+
+    # ---- end to end through the public API with HOST inputs: H2D of the batch + D2H of the loss every step ------
+    def step_e2e():
+        images.copy_(host[0], non_blocking=True)
+        calibs.copy_(host[1], non_blocking=True)
+        sizes.copy_(host[2], non_blocking=True)
+        step()
+        loss_host.copy_(loss_buf, non_blocking=True)
+    step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if ws > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+    h2d = sum(t.numel() * t.element_size() for t in host)
+
+    # ---- MSDA kernel duration in situ (eager steps, events around the launches; real sampling locations) --------
+    with MsdaProbe() as probe:
+        for _ in range(3):
+            fwd_bwd()
+        torch.cuda.synchronize()
+        enc_ms = probe.encoder_ms()
+    loss_val = float(loss_buf.item())
+
+    if rank != 0:
+        return None
+    pk = peaks()
+    fwd_bytes, _ = msda_bytes(B, FULL_S)
+    ms_step = total_ms / args.steps
+    line = {
+        "metric": METRIC, "value": B * ws * args.steps / (total_ms * 1e-3), "unit": "images/sec", "n_gpus": ws,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 storage, " + ("3xTF32 (fp32-equivalent)" if precision == "tf32x3" else "TF32") + " tensor-core math",
+        "data": "synthetic",
+        "config": {"workload": f"full MonoDETR fwd+bwd, ResNet-50, batch {B}/GPU, 1280x384 synthetic, train mode (550 queries, dropout 0.1), "
+                               f"surrogate loss, {'flat-bucket NCCL all-reduce, ' if ws > 1 else ''}precision={precision}",
+                   "parallelism": f"dp{ws}", "global_batch": B * ws,
+                   "timing": "CUDA events per step; 256 MiB L2 flush (untimed) between steps; " + ("CUDA graph replay" if graph is not None else "eager launches")},
+        "e2e": {"value": B * ws * args.steps / (e2e_ms * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+        "loss": loss_val,
+        "model_tflops": TRAIN_FLOPS_PER_IMAGE * B / (ms_step * 1e-3) / 1e12,
+        "tensor_frac_of_measured_bf16_peak": TRAIN_FLOPS_PER_IMAGE * B / (ms_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+    }
+    if enc_ms:
+        ach = fwd_bytes / (enc_ms * 1e-3) / 1e9
+        line["roofline"] = {"kernel": "msda_fwd_vec_kernel<8> (encoder call, Lq=10200, in situ)", "bound": "hbm", "achieved": ach,
+                            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                            "peak_source": pk["source"], "algorithmic_bytes": fwd_bytes, "avg_ms": enc_ms}
+    return line

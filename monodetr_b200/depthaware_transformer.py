@@ -233,6 +233,15 @@ class DepthAwareTransformer(nn.Module):
         constant_(self.reference_points.bias.data, 0.)
         normal_(self.level_embed)
 
+    def _shape_tensors(self, shapes, dev):
+        """int64 (L,2) shapes and (L,) level starts on the device, cached (no host->device copy per step; graph-safe)."""
+        key = (tuple(shapes), str(dev))
+        cache = self.__dict__.setdefault("_shape_cache", {})
+        if key not in cache:
+            ss = torch.as_tensor(shapes, dtype=torch.long, device=dev)
+            cache[key] = (ss, torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1])))
+        return cache[key]
+
     def forward(self, srcs, masks, pos_embeds, query_embed=None, depth_pos_embed=None, depth_pos_embed_ip=None, attn_mask=None):
         """srcs: list of NHWC maps (B, H_l, W_l, C); masks: None (all-False) or list of (B, H_l, W_l) bool;
         pos_embeds: list of (H_l*W_l, C); query_embed (nq, 2C); depth_pos_embed (B, HW1, C).
@@ -247,8 +256,7 @@ class DepthAwareTransformer(nn.Module):
         mask_flatten = None
         if masks is not None and any(m is not None and bool(m.any()) for m in masks):
             raise NotImplementedError("padding masks: this path always has all-False masks (backbone.py:88)")
-        spatial_shapes = torch.as_tensor(shapes, dtype=torch.long, device=dev)
-        level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+        spatial_shapes, level_start_index = self._shape_tensors(shapes, dev)
         memory = self.encoder(src_flatten, shapes, spatial_shapes, level_start_index, lvl_pos, mask_flatten)
         c = memory.shape[-1]
         query_pos, tgt = torch.split(query_embed, c, dim=1)
