@@ -284,7 +284,7 @@ def cpu_baseline_model():
     from oracle import monodetr_torch as om
 
     class A:
-        steps, warmup = 2, 1
+        steps, warmup, cpu_batch = 1, 0, 1
     val, dt, sample, threads, cfg = om.bench_reference_model(A)
     return {"value": val, "unit": "images/sec", "cores": threads, "kind": "port", "sample": sample + f", {A.steps} timed steps"}
 

@@ -6,13 +6,16 @@
 // are separate tensor-core GEMMs (conv_gemm.cu).
 //
 // Layout: q[b][i][h][32] with token stride ldq floats (so a packed QKV buffer can be passed), same for
-// k, v (ldk, ldv), out[b][i][h*32] contiguous-by-token with stride ldo.  key_padding_mask[b][j] (uint8,
-// nonzero = ignore) or null.  Dropout on the probabilities uses a counter-based hash RNG keyed by
-// (seed, b, h, i, j) so the backward pass regenerates the same mask.
+// k, v (ldk, ldv), out[b][i][h*32] with token stride ldo.  key_padding_mask[b][j] (uint8, nonzero = ignore) or
+// null.  Dropout on the probabilities uses a counter-based hash RNG keyed by (seed, b, h, i, j) so the backward
+// pass regenerates the same mask.
 //
-// v1 mapping (CUDA cores): 4 threads per query split the keys of each 64-key shared-memory tile,
-// each keeps q, an output accumulator and running (max, sum) in registers; partial results are merged
-// with shuffles.  Backward = a dQ kernel (same mapping) + a dK/dV kernel (4 threads per key over query tiles).
+// Mapping: register-resident warp-level tensor-core tiles (mma.sync m16n8k8 TF32, fp32 accumulate).  A CTA of
+// 4 warps owns 64 rows (queries, or keys in the dK/dV kernel); each warp owns 16 rows and streams 64-row tiles
+// of the other operand through padded shared memory (row stride 36 floats: conflict-free fragment loads).
+// Scores use error-compensated 3xTF32 (hi/lo split in registers) so exp() sees fp32-accurate logits; P.V uses
+// the same in the forward pass.  The P (C-fragment) -> A-fragment hand-off needs no shuffles: the k index of the
+// second GEMM is permuted (col t <-> key 2t, col t+4 <-> key 2t+1) and V/K/dO/Q rows are fetched in that order.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -22,120 +25,212 @@
 
 namespace {
 
-constexpr int HD = 32;         // head dim
-constexpr int TK = 64;         // tile of keys (fwd, dq) or queries (dkdv) staged in smem
+constexpr int HD = 32;             // head dim
+constexpr int BR = 64;             // rows per CTA (4 warps x 16)
+constexpr int BC = 64;             // streamed tile rows
+constexpr int LDS = 36;            // padded smem row stride (floats)
 constexpr int ATT_THREADS = 128;
-constexpr int ROWS_PER_CTA = ATT_THREADS / 4;   // 32 queries (or keys) per CTA
 
 struct AttnParams {
     const float *q, *k, *v;
-    const uint8_t* kpm;        // [B][Lk] or null
+    const uint8_t* kpm;            // [B][Lk] or null
     float* out;
-    float* lse;                // [B][H][Lq]
+    float* lse;                    // [B][H][Lq]
     int B, H, Lq, Lk, ldq, ldk, ldv, ldo;
-    float scale;               // 1/sqrt(d)
+    float scale;                   // 1/sqrt(d)
     float drop_p;
-    const unsigned long long* seed;   // device pointer (graph-safe), may be null when drop_p == 0
+    const unsigned long long* seed;
     unsigned long long site;
-    // backward
-    const float *dout, *o;     // dout / o with stride ldo
-    float* delta;              // [B][H][Lq]  (dO . O)
-    float *dq, *dk, *dv;       // strides lddq, lddk, lddv
+    const float *dout, *o;
+    float* delta;                  // [B][H][Lq]
+    float *dq, *dk, *dv;
     int lddq, lddk, lddv;
 };
 
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = f2tf32(x);
+    lo = f2tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// A fragments (16 rows x 32 cols) of a row-major global matrix: rows r0+g, r0+g+8; hi/lo split, optional scaling.
+struct AFrag {
+    uint32_t hi[4][4];
+    uint32_t lo[4][4];
+};
+__device__ __forceinline__ void load_afrag(AFrag& f, const float* base, int ld, int r0, int nrows, int lane, float mul) {
+    const int g = lane >> 2, t = lane & 3;
+    const int ra = r0 + g, rb = r0 + g + 8;
+    const float* pa = base + (size_t)min(ra, nrows - 1) * ld;
+    const float* pb = base + (size_t)min(rb, nrows - 1) * ld;
+    const float ma = ra < nrows ? mul : 0.f, mb = rb < nrows ? mul : 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        split_tf32(pa[ks * 8 + t] * ma, f.hi[ks][0], f.lo[ks][0]);
+        split_tf32(pb[ks * 8 + t] * mb, f.hi[ks][1], f.lo[ks][1]);
+        split_tf32(pa[ks * 8 + t + 4] * ma, f.hi[ks][2], f.lo[ks][2]);
+        split_tf32(pb[ks * 8 + t + 4] * mb, f.hi[ks][3], f.lo[ks][3]);
+    }
+}
+
+// C[16 x 64] = A[16 x 32] . S^T, S = smem tile [64][LDS] (rows = the 64 output columns).  NS = 3: error-compensated.
+template <int NS>
+__device__ __forceinline__ void gemm_nt(float (&c)[8][4], const AFrag& a, const float (*s)[LDS], int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const float b0f = s[nt * 8 + g][ks * 8 + t], b1f = s[nt * 8 + g][ks * 8 + t + 4];
+            uint32_t b0h, b0l, b1h, b1l;
+            split_tf32(b0f, b0h, b0l);
+            split_tf32(b1f, b1h, b1l);
+            if (NS == 3) {
+                mma8(c[nt], a.lo[ks], b0h, b1h);
+                mma8(c[nt], a.hi[ks], b0l, b1l);
+            }
+            mma8(c[nt], a.hi[ks], b0h, b1h);
+        }
+    }
+}
+
+// acc[16 x 32] += P[16 x 64] . S, P given as C fragments (cols 2t,2t+1 of each 8-wide tile), S = smem [64][LDS].
+// k-permutation trick: A col t <-> key 2t, A col t+4 <-> key 2t+1, so A = (c0, c2, c1, c3) and B rows 2t / 2t+1.
+template <int NS>
+__device__ __forceinline__ void gemm_nn(float (&acc)[4][4], const float (&p)[8][4], const float (*s)[LDS], int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int kt = 0; kt < 8; ++kt) {
+        uint32_t ah[4], al[4];
+        split_tf32(p[kt][0], ah[0], al[0]);
+        split_tf32(p[kt][2], ah[1], al[1]);
+        split_tf32(p[kt][1], ah[2], al[2]);
+        split_tf32(p[kt][3], ah[3], al[3]);
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn) {
+            const float b0f = s[kt * 8 + 2 * t][dn * 8 + g], b1f = s[kt * 8 + 2 * t + 1][dn * 8 + g];
+            uint32_t b0h, b0l, b1h, b1l;
+            split_tf32(b0f, b0h, b0l);
+            split_tf32(b1f, b1h, b1l);
+            if (NS == 3) {
+                mma8(acc[dn], al, b0h, b1h);
+                mma8(acc[dn], ah, b0l, b1l);
+            }
+            mma8(acc[dn], ah, b0h, b1h);
+        }
+    }
+}
+
+// cooperative load of a [64][32] tile (rows r0.., zero beyond nrows) into padded smem
+__device__ __forceinline__ void load_tile(float (*s)[LDS], const float* base, int ld, int r0, int nrows) {
+    for (int i = threadIdx.x; i < BC * (HD / 4); i += ATT_THREADS) {
+        const int r = i >> 3, c = (i & 7) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r0 + r < nrows) v = *reinterpret_cast<const float4*>(base + (size_t)(r0 + r) * ld + c);
+        *reinterpret_cast<float4*>(&s[r][c]) = v;
+    }
+}
+
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
 __device__ __forceinline__ float quad_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    return v;
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
-__device__ __forceinline__ bool keep_elem(const AttnParams& p, unsigned long long seed, int b, int h, int i, int j) {
+__device__ __forceinline__ float keep_scale(const AttnParams& p, unsigned long long seed, int b, int h, int i, int j, float inv_keep) {
     const unsigned long long idx = (((unsigned long long)(b * p.H + h) * p.Lq + i) * (unsigned long long)p.Lk + j);
-    return mdb::rng_uniform(seed, idx) >= p.drop_p;
+    return mdb::rng_uniform(seed, idx) >= p.drop_p ? inv_keep : 0.f;
 }
 
+// ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_kernel(const AttnParams p) {
-    __shared__ __align__(16) float sK[TK][HD];
-    __shared__ __align__(16) float sV[TK][HD];
+    __shared__ __align__(16) float sK[BC][LDS];
+    __shared__ __align__(16) float sV[BC][LDS];
     const int b = blockIdx.z, h = blockIdx.y;
-    const int qi = blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 2);
-    const int kq = threadIdx.x & 3;
-    const bool qok = qi < p.Lq;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = blockIdx.x * BR + warp * 16;
+    const float* qb = p.q + (size_t)b * p.Lq * p.ldq + h * HD;
+    const float* kb = p.k + (size_t)b * p.Lk * p.ldk + h * HD;
+    const float* vb = p.v + (size_t)b * p.Lk * p.ldv + h * HD;
     const unsigned long long seed = (p.drop_p > 0.f) ? (*p.seed + p.site * 0x9E3779B97F4A7C15ull) : 0ull;
     const float inv_keep = 1.f / (1.f - p.drop_p);
+    AFrag qa;
+    load_afrag(qa, qb, p.ldq, r0, p.Lq, lane, p.scale);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;      // rows g and g+8
+    const int qi0 = r0 + g, qi1 = r0 + g + 8;
 
-    float q[HD], acc[HD];
-    {
-        const float* qp = p.q + ((size_t)b * p.Lq + (qok ? qi : 0)) * p.ldq + h * HD;
-#pragma unroll
-        for (int d = 0; d < HD; d += 4) {
-            const float4 t = *reinterpret_cast<const float4*>(qp + d);
-            q[d] = t.x * p.scale; q[d + 1] = t.y * p.scale; q[d + 2] = t.z * p.scale; q[d + 3] = t.w * p.scale;
-        }
-#pragma unroll
-        for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-    }
-    float m = -INFINITY, l = 0.f;
-
-    for (int k0 = 0; k0 < p.Lk; k0 += TK) {
+    for (int k0 = 0; k0 < p.Lk; k0 += BC) {
         __syncthreads();
-        for (int t = threadIdx.x; t < TK * HD / 4; t += ATT_THREADS) {
-            const int r = t / (HD / 4), c = (t % (HD / 4)) * 4;
-            const int j = k0 + r;
-            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-            if (j < p.Lk) {
-                kv = *reinterpret_cast<const float4*>(p.k + ((size_t)b * p.Lk + j) * p.ldk + h * HD + c);
-                vv = *reinterpret_cast<const float4*>(p.v + ((size_t)b * p.Lk + j) * p.ldv + h * HD + c);
-            }
-            *reinterpret_cast<float4*>(&sK[r][c]) = kv;
-            *reinterpret_cast<float4*>(&sV[r][c]) = vv;
-        }
+        load_tile(sK, kb, p.ldk, k0, p.Lk);
+        load_tile(sV, vb, p.ldv, k0, p.Lk);
         __syncthreads();
-        const int jmax = min(TK, p.Lk - k0);
-        for (int r = kq; r < jmax; r += 4) {
-            const int j = k0 + r;
-            if (p.kpm && p.kpm[(size_t)b * p.Lk + j]) continue;
-            float s = 0.f;
+        float s[8][4];
+        gemm_nt<3>(s, qa, sK, lane);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-            for (int d = 0; d < HD; d += 4) {
-                const float4 kk = *reinterpret_cast<const float4*>(&sK[r][d]);
-                s = fmaf(q[d], kk.x, s); s = fmaf(q[d + 1], kk.y, s); s = fmaf(q[d + 2], kk.z, s); s = fmaf(q[d + 3], kk.w, s);
-            }
-            const float mn = fmaxf(m, s);
-            const float corr = __expf(m - mn);       // exp(-inf) = 0 on the first key
-            const float pe = __expf(s - mn);
-            l = l * corr + pe;
-            float pw = pe;
-            if (p.drop_p > 0.f) pw = keep_elem(p, seed, b, h, qi, j) ? pe * inv_keep : 0.f;
+        for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-            for (int d = 0; d < HD; d += 4) {
-                const float4 vv = *reinterpret_cast<const float4*>(&sV[r][d]);
-                acc[d] = fmaf(acc[d], corr, pw * vv.x);
-                acc[d + 1] = fmaf(acc[d + 1], corr, pw * vv.y);
-                acc[d + 2] = fmaf(acc[d + 2], corr, pw * vv.z);
-                acc[d + 3] = fmaf(acc[d + 3], corr, pw * vv.w);
+            for (int e = 0; e < 2; ++e) {
+                const int j = k0 + nt * 8 + 2 * t + e;
+                const bool dead = (j >= p.Lk) || (p.kpm && p.kpm[(size_t)b * p.Lk + min(j, p.Lk - 1)]);
+                if (dead) { s[nt][e] = -INFINITY; s[nt][2 + e] = -INFINITY; }
+                mx0 = fmaxf(mx0, s[nt][e]);
+                mx1 = fmaxf(mx1, s[nt][2 + e]);
             }
-            m = mn;
         }
+        const float mn0 = fmaxf(m0, quad_max(mx0)), mn1 = fmaxf(m1, quad_max(mx1));
+        const float c0 = (mn0 == -INFINITY) ? 1.f : __expf(m0 - mn0), c1 = (mn1 == -INFINITY) ? 1.f : __expf(m1 - mn1);
+        l0 *= c0; l1 *= c1;
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn) { acc[dn][0] *= c0; acc[dn][1] *= c0; acc[dn][2] *= c1; acc[dn][3] *= c1; }
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = k0 + nt * 8 + 2 * t + e;
+                float p0 = (mn0 == -INFINITY) ? 0.f : __expf(s[nt][e] - mn0);
+                float p1 = (mn1 == -INFINITY) ? 0.f : __expf(s[nt][2 + e] - mn1);
+                l0 += p0; l1 += p1;
+                if (p.drop_p > 0.f) {
+                    p0 *= keep_scale(p, seed, b, h, qi0, j, inv_keep);
+                    p1 *= keep_scale(p, seed, b, h, qi1, j, inv_keep);
+                }
+                s[nt][e] = p0; s[nt][2 + e] = p1;
+            }
+        }
+        m0 = mn0; m1 = mn1;
+        gemm_nn<3>(acc, s, sV, lane);
     }
-    // merge the 4 key-partitions of each query
-    float mall = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    mall = fmaxf(mall, __shfl_xor_sync(0xffffffffu, mall, 2));
-    const float f = (m == -INFINITY) ? 0.f : __expf(m - mall);
-    const float lall = quad_sum(l * f);
-    const float inv = lall > 0.f ? 1.f / lall : 0.f;
+    l0 = quad_sum(l0); l1 = quad_sum(l1);
+    const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+    float* ob = p.out + (size_t)b * p.Lq * p.ldo + h * HD;
 #pragma unroll
-    for (int d = 0; d < HD; ++d) acc[d] = quad_sum(acc[d] * f) * inv;
-    if (qok) {
-        float* op = p.out + ((size_t)b * p.Lq + qi) * p.ldo + h * HD;
-        // each of the 4 threads writes 8 of the 32 channels
-#pragma unroll
-        for (int d = 0; d < HD; d += 4) {
-            if ((d >> 3) == kq) *reinterpret_cast<float4*>(op + d) = make_float4(acc[d], acc[d + 1], acc[d + 2], acc[d + 3]);
-        }
-        if (kq == 0) p.lse[((size_t)b * p.H + h) * p.Lq + qi] = (lall > 0.f) ? (mall + __logf(lall)) : -INFINITY;
+    for (int dn = 0; dn < 4; ++dn) {
+        if (qi0 < p.Lq) *reinterpret_cast<float2*>(ob + (size_t)qi0 * p.ldo + dn * 8 + 2 * t) = make_float2(acc[dn][0] * i0, acc[dn][1] * i0);
+        if (qi1 < p.Lq) *reinterpret_cast<float2*>(ob + (size_t)qi1 * p.ldo + dn * 8 + 2 * t) = make_float2(acc[dn][2] * i1, acc[dn][3] * i1);
+    }
+    if (t == 0) {
+        float* lp = p.lse + ((size_t)b * p.H + h) * p.Lq;
+        if (qi0 < p.Lq) lp[qi0] = l0 > 0.f ? m0 + __logf(l0) : -INFINITY;
+        if (qi1 < p.Lq) lp[qi1] = l1 > 0.f ? m1 + __logf(l1) : -INFINITY;
     }
 }
 
@@ -160,157 +255,146 @@ __global__ void attn_delta_kernel(const AttnParams p) {
     p.delta[((size_t)b * p.H + h) * p.Lq + i] = s;
 }
 
+// dQ: CTA = 64 queries, streams key/value tiles.
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dq_kernel(const AttnParams p) {
-    __shared__ __align__(16) float sK[TK][HD];
-    __shared__ __align__(16) float sV[TK][HD];
+    __shared__ __align__(16) float sK[BC][LDS];
+    __shared__ __align__(16) float sV[BC][LDS];
     const int b = blockIdx.z, h = blockIdx.y;
-    const int qi = blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 2);
-    const int kq = threadIdx.x & 3;
-    const bool qok = qi < p.Lq;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = blockIdx.x * BR + warp * 16;
+    const float* qb = p.q + (size_t)b * p.Lq * p.ldq + h * HD;
+    const float* gb = p.dout + (size_t)b * p.Lq * p.ldo + h * HD;
+    const float* kb = p.k + (size_t)b * p.Lk * p.ldk + h * HD;
+    const float* vb = p.v + (size_t)b * p.Lk * p.ldv + h * HD;
     const unsigned long long seed = (p.drop_p > 0.f) ? (*p.seed + p.site * 0x9E3779B97F4A7C15ull) : 0ull;
     const float inv_keep = 1.f / (1.f - p.drop_p);
-    float q[HD], go[HD], dq[HD];
-    const size_t row = (size_t)b * p.Lq + (qok ? qi : 0);
-    {
-        const float* qp = p.q + row * p.ldq + h * HD;
-        const float* gp = p.dout + row * p.ldo + h * HD;
+    AFrag qa, ga;
+    load_afrag(qa, qb, p.ldq, r0, p.Lq, lane, p.scale);
+    load_afrag(ga, gb, p.ldo, r0, p.Lq, lane, 1.f);
+    const int qi0 = r0 + g, qi1 = r0 + g + 8;
+    const size_t st = ((size_t)b * p.H + h) * p.Lq;
+    const float lse0 = qi0 < p.Lq ? p.lse[st + qi0] : INFINITY, lse1 = qi1 < p.Lq ? p.lse[st + qi1] : INFINITY;
+    const float dl0 = qi0 < p.Lq ? p.delta[st + qi0] : 0.f, dl1 = qi1 < p.Lq ? p.delta[st + qi1] : 0.f;
+    float acc[4][4];
 #pragma unroll
-        for (int d = 0; d < HD; ++d) { q[d] = qp[d] * p.scale; go[d] = gp[d]; dq[d] = 0.f; }
-    }
-    const size_t st = ((size_t)b * p.H + h) * p.Lq + (qok ? qi : 0);
-    const float lse = p.lse[st], delta = p.delta[st];
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 
-    for (int k0 = 0; k0 < p.Lk; k0 += TK) {
+    for (int k0 = 0; k0 < p.Lk; k0 += BC) {
         __syncthreads();
-        for (int t = threadIdx.x; t < TK * HD / 4; t += ATT_THREADS) {
-            const int r = t / (HD / 4), c = (t % (HD / 4)) * 4;
-            const int j = k0 + r;
-            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-            if (j < p.Lk) {
-                kv = *reinterpret_cast<const float4*>(p.k + ((size_t)b * p.Lk + j) * p.ldk + h * HD + c);
-                vv = *reinterpret_cast<const float4*>(p.v + ((size_t)b * p.Lk + j) * p.ldv + h * HD + c);
-            }
-            *reinterpret_cast<float4*>(&sK[r][c]) = kv;
-            *reinterpret_cast<float4*>(&sV[r][c]) = vv;
-        }
+        load_tile(sK, kb, p.ldk, k0, p.Lk);
+        load_tile(sV, vb, p.ldv, k0, p.Lk);
         __syncthreads();
-        const int jmax = min(TK, p.Lk - k0);
-        for (int r = kq; r < jmax; r += 4) {
-            const int j = k0 + r;
-            if (p.kpm && p.kpm[(size_t)b * p.Lk + j]) continue;
-            float s = 0.f, dp = 0.f;
+        float s[8][4], dp[8][4];
+        gemm_nt<3>(s, qa, sK, lane);
+        gemm_nt<1>(dp, ga, sV, lane);
 #pragma unroll
-            for (int d = 0; d < HD; d += 4) {
-                const float4 kk = *reinterpret_cast<const float4*>(&sK[r][d]);
-                const float4 vv = *reinterpret_cast<const float4*>(&sV[r][d]);
-                s = fmaf(q[d], kk.x, s); s = fmaf(q[d + 1], kk.y, s); s = fmaf(q[d + 2], kk.z, s); s = fmaf(q[d + 3], kk.w, s);
-                dp = fmaf(go[d], vv.x, dp); dp = fmaf(go[d + 1], vv.y, dp); dp = fmaf(go[d + 2], vv.z, dp); dp = fmaf(go[d + 3], vv.w, dp);
-            }
-            const float pe = (lse == -INFINITY) ? 0.f : __expf(s - lse);
-            if (p.drop_p > 0.f) dp = keep_elem(p, seed, b, h, qi, j) ? dp * inv_keep : 0.f;
-            const float ds = pe * (dp - delta);
+        for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-            for (int d = 0; d < HD; d += 4) {
-                const float4 kk = *reinterpret_cast<const float4*>(&sK[r][d]);
-                dq[d] = fmaf(ds, kk.x, dq[d]); dq[d + 1] = fmaf(ds, kk.y, dq[d + 1]);
-                dq[d + 2] = fmaf(ds, kk.z, dq[d + 2]); dq[d + 3] = fmaf(ds, kk.w, dq[d + 3]);
+            for (int e = 0; e < 2; ++e) {
+                const int j = k0 + nt * 8 + 2 * t + e;
+                const bool dead = (j >= p.Lk) || (p.kpm && p.kpm[(size_t)b * p.Lk + min(j, p.Lk - 1)]);
+                float p0 = (dead || lse0 == -INFINITY) ? 0.f : __expf(s[nt][e] - lse0);
+                float p1 = (dead || lse1 == -INFINITY) ? 0.f : __expf(s[nt][2 + e] - lse1);
+                float d0 = dp[nt][e], d1 = dp[nt][2 + e];
+                if (p.drop_p > 0.f) {
+                    d0 *= keep_scale(p, seed, b, h, qi0, j, inv_keep);
+                    d1 *= keep_scale(p, seed, b, h, qi1, j, inv_keep);
+                }
+                s[nt][e] = p0 * (d0 - dl0);
+                s[nt][2 + e] = p1 * (d1 - dl1);
             }
         }
+        gemm_nn<1>(acc, s, sK, lane);
     }
+    float* ob = p.dq + (size_t)b * p.Lq * p.lddq + h * HD;
 #pragma unroll
-    for (int d = 0; d < HD; ++d) dq[d] = quad_sum(dq[d]) * p.scale;
-    if (qok) {
-        float* op = p.dq + row * p.lddq + h * HD;
-#pragma unroll
-        for (int d = 0; d < HD; d += 4)
-            if ((d >> 3) == kq) *reinterpret_cast<float4*>(op + d) = make_float4(dq[d], dq[d + 1], dq[d + 2], dq[d + 3]);
+    for (int dn = 0; dn < 4; ++dn) {
+        if (qi0 < p.Lq) *reinterpret_cast<float2*>(ob + (size_t)qi0 * p.lddq + dn * 8 + 2 * t) = make_float2(acc[dn][0] * p.scale, acc[dn][1] * p.scale);
+        if (qi1 < p.Lq) *reinterpret_cast<float2*>(ob + (size_t)qi1 * p.lddq + dn * 8 + 2 * t) = make_float2(acc[dn][2] * p.scale, acc[dn][3] * p.scale);
     }
 }
 
+// dK / dV: CTA = 64 keys, streams query tiles (Q, dO, lse, delta).
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dkv_kernel(const AttnParams p) {
-    __shared__ __align__(16) float sQ[TK][HD];
-    __shared__ __align__(16) float sG[TK][HD];
-    __shared__ float sL[TK], sD[TK];
+    __shared__ __align__(16) float sQ[BC][LDS];
+    __shared__ __align__(16) float sG[BC][LDS];
+    __shared__ float sL[BC], sD[BC];
     const int b = blockIdx.z, h = blockIdx.y;
-    const int kj = blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 2);
-    const int part = threadIdx.x & 3;
-    const bool kok = kj < p.Lk;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = blockIdx.x * BR + warp * 16;                      // first key row of this warp
+    const float* qb = p.q + (size_t)b * p.Lq * p.ldq + h * HD;
+    const float* gb = p.dout + (size_t)b * p.Lq * p.ldo + h * HD;
+    const float* kb = p.k + (size_t)b * p.Lk * p.ldk + h * HD;
+    const float* vb = p.v + (size_t)b * p.Lk * p.ldv + h * HD;
     const unsigned long long seed = (p.drop_p > 0.f) ? (*p.seed + p.site * 0x9E3779B97F4A7C15ull) : 0ull;
     const float inv_keep = 1.f / (1.f - p.drop_p);
-    float kk[HD], vv[HD], dk[HD], dv[HD];
-    const size_t row = (size_t)b * p.Lk + (kok ? kj : 0);
-    {
-        const float* kp = p.k + row * p.ldk + h * HD;
-        const float* vp = p.v + row * p.ldv + h * HD;
+    AFrag ka, va;
+    load_afrag(ka, kb, p.ldk, r0, p.Lk, lane, p.scale);
+    load_afrag(va, vb, p.ldv, r0, p.Lk, lane, 1.f);
+    const int kj0 = r0 + g, kj1 = r0 + g + 8;
+    const bool dead0 = kj0 >= p.Lk || (p.kpm && p.kpm[(size_t)b * p.Lk + min(kj0, p.Lk - 1)]);
+    const bool dead1 = kj1 >= p.Lk || (p.kpm && p.kpm[(size_t)b * p.Lk + min(kj1, p.Lk - 1)]);
+    float dk[4][4], dv[4][4];
 #pragma unroll
-        for (int d = 0; d < HD; ++d) { kk[d] = kp[d]; vv[d] = vp[d]; dk[d] = 0.f; dv[d] = 0.f; }
+    for (int i = 0; i < 4; ++i) {
+        dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+        dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
     }
-    const bool masked = !kok || (p.kpm && p.kpm[(size_t)b * p.Lk + kj]);
+    const size_t st = ((size_t)b * p.H + h) * p.Lq;
 
-    for (int q0 = 0; q0 < p.Lq; q0 += TK) {
+    for (int q0 = 0; q0 < p.Lq; q0 += BC) {
         __syncthreads();
-        for (int t = threadIdx.x; t < TK * HD / 4; t += ATT_THREADS) {
-            const int r = t / (HD / 4), c = (t % (HD / 4)) * 4;
-            const int i = q0 + r;
-            float4 qv = make_float4(0.f, 0.f, 0.f, 0.f), gv = qv;
-            if (i < p.Lq) {
-                qv = *reinterpret_cast<const float4*>(p.q + ((size_t)b * p.Lq + i) * p.ldq + h * HD + c);
-                gv = *reinterpret_cast<const float4*>(p.dout + ((size_t)b * p.Lq + i) * p.ldo + h * HD + c);
-            }
-            *reinterpret_cast<float4*>(&sQ[r][c]) = qv;
-            *reinterpret_cast<float4*>(&sG[r][c]) = gv;
-        }
-        for (int t = threadIdx.x; t < TK; t += ATT_THREADS) {
-            const int i = q0 + t;
-            const size_t st = ((size_t)b * p.H + h) * p.Lq + min(i, p.Lq - 1);
-            sL[t] = (i < p.Lq) ? p.lse[st] : INFINITY;
-            sD[t] = (i < p.Lq) ? p.delta[st] : 0.f;
+        load_tile(sQ, qb, p.ldq, q0, p.Lq);
+        load_tile(sG, gb, p.ldo, q0, p.Lq);
+        if (threadIdx.x < BC) {
+            const int i = q0 + threadIdx.x;
+            sL[threadIdx.x] = i < p.Lq ? p.lse[st + i] : INFINITY;     // +inf -> p = 0 for rows past the end
+            sD[threadIdx.x] = i < p.Lq ? p.delta[st + i] : 0.f;
         }
         __syncthreads();
-        if (masked) continue;
-        const int imax = min(TK, p.Lq - q0);
-        for (int r = part; r < imax; r += 4) {
-            const int i = q0 + r;
-            float s = 0.f, dp = 0.f;
+        float s[8][4], dp[8][4];
+        gemm_nt<3>(s, ka, sQ, lane);          // S^T[key][query] (already scaled through K)
+        gemm_nt<1>(dp, va, sG, lane);         // dP^T[key][query] = V . dO^T
+        float pd[8][4];                        // dropped probabilities for dV
 #pragma unroll
-            for (int d = 0; d < HD; d += 4) {
-                const float4 qq = *reinterpret_cast<const float4*>(&sQ[r][d]);
-                const float4 gg = *reinterpret_cast<const float4*>(&sG[r][d]);
-                s = fmaf(qq.x, kk[d], s); s = fmaf(qq.y, kk[d + 1], s); s = fmaf(qq.z, kk[d + 2], s); s = fmaf(qq.w, kk[d + 3], s);
-                dp = fmaf(gg.x, vv[d], dp); dp = fmaf(gg.y, vv[d + 1], dp); dp = fmaf(gg.z, vv[d + 2], dp); dp = fmaf(gg.w, vv[d + 3], dp);
-            }
-            const float pe = (sL[r] == -INFINITY) ? 0.f : __expf(s * p.scale - sL[r]);
-            float pw = pe;
-            if (p.drop_p > 0.f) {
-                const bool keep = keep_elem(p, seed, b, h, i, kj);
-                pw = keep ? pe * inv_keep : 0.f;
-                dp = keep ? dp * inv_keep : 0.f;
-            }
-            const float ds = pe * (dp - sD[r]) * p.scale;
+        for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-            for (int d = 0; d < HD; d += 4) {
-                const float4 qq = *reinterpret_cast<const float4*>(&sQ[r][d]);
-                const float4 gg = *reinterpret_cast<const float4*>(&sG[r][d]);
-                dk[d] = fmaf(ds, qq.x, dk[d]); dk[d + 1] = fmaf(ds, qq.y, dk[d + 1]);
-                dk[d + 2] = fmaf(ds, qq.z, dk[d + 2]); dk[d + 3] = fmaf(ds, qq.w, dk[d + 3]);
-                dv[d] = fmaf(pw, gg.x, dv[d]); dv[d + 1] = fmaf(pw, gg.y, dv[d + 1]);
-                dv[d + 2] = fmaf(pw, gg.z, dv[d + 2]); dv[d + 3] = fmaf(pw, gg.w, dv[d + 3]);
+            for (int e = 0; e < 2; ++e) {
+                const int il = nt * 8 + 2 * t + e, i = q0 + il;
+                const float lse = sL[il], dl = sD[il];
+                const bool nolse = (lse == -INFINITY);
+                float p0 = (dead0 || nolse) ? 0.f : __expf(s[nt][e] - lse);
+                float p1 = (dead1 || nolse) ? 0.f : __expf(s[nt][2 + e] - lse);
+                float d0 = dp[nt][e], d1 = dp[nt][2 + e];
+                float w0 = p0, w1 = p1;
+                if (p.drop_p > 0.f) {
+                    const float k0s = keep_scale(p, seed, b, h, i, kj0, inv_keep), k1s = keep_scale(p, seed, b, h, i, kj1, inv_keep);
+                    w0 *= k0s; w1 *= k1s; d0 *= k0s; d1 *= k1s;
+                }
+                pd[nt][e] = w0; pd[nt][2 + e] = w1;
+                s[nt][e] = p0 * (d0 - dl);
+                s[nt][2 + e] = p1 * (d1 - dl);
             }
         }
+        gemm_nn<1>(dv, pd, sG, lane);          // dV += P^T_dropped . dO
+        gemm_nn<1>(dk, s, sQ, lane);           // dK += dS^T . Q
     }
+    float* dkb = p.dk + (size_t)b * p.Lk * p.lddk + h * HD;
+    float* dvb = p.dv + (size_t)b * p.Lk * p.lddv + h * HD;
 #pragma unroll
-    for (int d = 0; d < HD; ++d) { dk[d] = quad_sum(dk[d]); dv[d] = quad_sum(dv[d]); }
-    if (kok) {
-        float* dkp = p.dk + row * p.lddk + h * HD;
-        float* dvp = p.dv + row * p.lddv + h * HD;
-#pragma unroll
-        for (int d = 0; d < HD; d += 4)
-            if ((d >> 3) == part) {
-                *reinterpret_cast<float4*>(dkp + d) = make_float4(dk[d], dk[d + 1], dk[d + 2], dk[d + 3]);
-                *reinterpret_cast<float4*>(dvp + d) = make_float4(dv[d], dv[d + 1], dv[d + 2], dv[d + 3]);
-            }
+    for (int dn = 0; dn < 4; ++dn) {
+        if (kj0 < p.Lk) {
+            *reinterpret_cast<float2*>(dkb + (size_t)kj0 * p.lddk + dn * 8 + 2 * t) = make_float2(dk[dn][0] * p.scale, dk[dn][1] * p.scale);
+            *reinterpret_cast<float2*>(dvb + (size_t)kj0 * p.lddv + dn * 8 + 2 * t) = make_float2(dv[dn][0], dv[dn][1]);
+        }
+        if (kj1 < p.Lk) {
+            *reinterpret_cast<float2*>(dkb + (size_t)kj1 * p.lddk + dn * 8 + 2 * t) = make_float2(dk[dn][2] * p.scale, dk[dn][3] * p.scale);
+            *reinterpret_cast<float2*>(dvb + (size_t)kj1 * p.lddv + dn * 8 + 2 * t) = make_float2(dv[dn][2], dv[dn][3]);
+        }
     }
 }
 
@@ -339,7 +423,7 @@ int mdb_attention_forward_f32(const float* q, const float* k, const float* v, co
     p.scale = 1.f / sqrtf((float)HD); p.drop_p = drop_p; p.seed = seed; p.site = site;
     int rc = check(p);
     if (rc) return rc;
-    dim3 grid((Lq + ROWS_PER_CTA - 1) / ROWS_PER_CTA, H, B);
+    dim3 grid((Lq + BR - 1) / BR, H, B);
     attn_fwd_kernel<<<grid, ATT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
     return (int)cudaGetLastError();
 }
@@ -363,8 +447,8 @@ int mdb_attention_backward_f32(const float* q, const float* k, const float* v, c
     if ((lddq | lddk | lddv) % 4) return MDB_EINVAL;
     const long long n = (long long)B * Lq * H;
     attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
-    attn_bwd_dq_kernel<<<dim3((Lq + ROWS_PER_CTA - 1) / ROWS_PER_CTA, H, B), ATT_THREADS, 0, stream>>>(p);
-    attn_bwd_dkv_kernel<<<dim3((Lk + ROWS_PER_CTA - 1) / ROWS_PER_CTA, H, B), ATT_THREADS, 0, stream>>>(p);
+    attn_bwd_dq_kernel<<<dim3((Lq + BR - 1) / BR, H, B), ATT_THREADS, 0, stream>>>(p);
+    attn_bwd_dkv_kernel<<<dim3((Lk + BR - 1) / BR, H, B), ATT_THREADS, 0, stream>>>(p);
     return (int)cudaGetLastError();
 }
 

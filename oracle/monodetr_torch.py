@@ -433,9 +433,9 @@ def surrogate_loss(out):
 
 def bench_reference_model(args):
     """`bench.py --impl reference --workload model`: train-shape forward+backward of this CPU port on a bounded sample."""
-    threads = os.cpu_count()
+    threads = min(os.cpu_count(), int(os.environ.get("MDB_CPU_THREADS", "32")))   # torch CPU ops stop scaling (and regress) beyond ~32 threads
     torch.set_num_threads(threads)
-    Bs = 2
+    Bs = getattr(args, "cpu_batch", 2)
     sd = deterministic_state_dict()
     trainable = [k for k in sd if sd[k].dtype.is_floating_point and "running_" not in k and "depth_bin_values" not in k
                  and not (k.startswith("backbone.0.body.") and not any(s in k for s in ("layer2", "layer3", "layer4")))
