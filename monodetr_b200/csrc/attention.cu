@@ -288,7 +288,7 @@ attn_bwd_dq_kernel(const AttnParams p) {
         __syncthreads();
         float s[8][4], dp[8][4];
         gemm_nt<3>(s, qa, sK, lane);
-        gemm_nt<1>(dp, ga, sV, lane);
+        gemm_nt<3>(dp, ga, sV, lane);
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -306,7 +306,7 @@ attn_bwd_dq_kernel(const AttnParams p) {
                 s[nt][2 + e] = p1 * (d1 - dl1);
             }
         }
-        gemm_nn<1>(acc, s, sK, lane);
+        gemm_nn<3>(acc, s, sK, lane);
     }
     float* ob = p.dq + (size_t)b * p.Lq * p.lddq + h * HD;
 #pragma unroll
@@ -358,7 +358,7 @@ attn_bwd_dkv_kernel(const AttnParams p) {
         __syncthreads();
         float s[8][4], dp[8][4];
         gemm_nt<3>(s, ka, sQ, lane);          // S^T[key][query] (already scaled through K)
-        gemm_nt<1>(dp, va, sG, lane);         // dP^T[key][query] = V . dO^T
+        gemm_nt<3>(dp, va, sG, lane);         // dP^T[key][query] = V . dO^T
         float pd[8][4];                        // dropped probabilities for dV
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
@@ -380,8 +380,8 @@ attn_bwd_dkv_kernel(const AttnParams p) {
                 s[nt][2 + e] = p1 * (d1 - dl);
             }
         }
-        gemm_nn<1>(dv, pd, sG, lane);          // dV += P^T_dropped . dO
-        gemm_nn<1>(dk, s, sQ, lane);           // dK += dS^T . Q
+        gemm_nn<3>(dv, pd, sG, lane);          // dV += P^T_dropped . dO
+        gemm_nn<3>(dk, s, sQ, lane);           // dK += dS^T . Q
     }
     float* dkb = p.dk + (size_t)b * p.Lk * p.lddk + h * HD;
     float* dvb = p.dv + (size_t)b * p.Lk * p.lddv + h * HD;

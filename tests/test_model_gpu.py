@@ -82,6 +82,8 @@ def test_backward_matches_oracle_gradients():
     for name, p in m.named_parameters():
         if name.startswith("depthaware_transformer.decoder.bbox_embed") or name.startswith("depthaware_transformer.decoder.dim_embed"):
             continue
+        if not p.requires_grad:
+            continue
         gref = sd[name].grad if name in sd else None
         if p.grad is None:
             assert gref is None or float(gref.abs().max()) == 0.0, f"{name}: missing gradient"

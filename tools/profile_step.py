@@ -1,0 +1,34 @@
+"""One eager train step of the model under `ncu --profile-from-start off` (cudaProfilerStart/Stop around step 2)."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from monodetr_b200 import build_monodetr, kernels as K, tc  # noqa: E402
+from monodetr_b200.bench_model import surrogate_loss, synthetic_batch  # noqa: E402
+from monodetr_b200.monodetr import DEFAULT_MODEL_CFG  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+tc.set_precision(os.environ.get("MDB_PRECISION", "tf32x3"))
+torch.manual_seed(0)
+model, _ = build_monodetr(DEFAULT_MODEL_CFG)
+model = model.cuda().train()
+images, calibs, sizes = (t.cuda() for t in synthetic_batch(B, 1))
+
+
+def step():
+    for p in model.parameters():
+        p.grad = None
+    K.advance_seed(images.device)
+    out = model(images, calibs, None, sizes)
+    surrogate_loss(out).backward()
+
+
+step()
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+step()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
