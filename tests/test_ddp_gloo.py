@@ -1,0 +1,60 @@
+"""CPU, world_size 2, gloo: the flat-bucket gradient all-reduce (monodetr_b200/ddp.py) -- host logic of the N>1 path."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from monodetr_b200.ddp import FlatGradBucket, broadcast_parameters
+    torch.manual_seed(rank)                       # different init per rank -> broadcast must equalise
+    model = torch.nn.ModuleDict({
+        "a": torch.nn.Linear(8, 4),
+        "sa_v_proj": torch.nn.Linear(4, 4),       # never-used tensors stay out of the bucket
+        "b": torch.nn.Linear(4, 2),
+    })
+    broadcast_parameters(model)
+    w0 = model["a"].weight.detach().clone()
+    bucket = FlatGradBucket(model)
+    assert bucket.numel == sum(p.numel() for n, p in model.named_parameters() if "sa_v_proj" not in n)
+    assert model["sa_v_proj"].weight.grad is None
+    bucket.zero()
+    x = torch.full((3, 8), float(rank + 1))
+    model["b"](model["a"](x)).sum().backward()   # accumulates straight into the flat views
+    local = bucket.flat.clone()
+    assert local.abs().sum() > 0
+    bucket.all_reduce()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    expect = sum(gathered) / world
+    ok = torch.allclose(bucket.flat, expect, atol=1e-6) and model["a"].weight.grad.data_ptr() == bucket.flat.data_ptr()
+    q.put((rank, bool(ok), w0))
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)
+    assert torch.equal(res[0][2], res[1][2])      # parameters were broadcast from rank 0
