@@ -44,6 +44,7 @@ struct TcParams {
     int tap_dy[kMaxTaps], tap_dx[kMaxTaps], tap_w[kMaxTaps];
     // ---- wgrad: reduction over pixel tiles of 32 (rth x rtw), split across blockIdx.z ----------
     int rtiles_x, rtiles_y, rtw, rth, n_img, red_per_split;
+    int total_tiles, n_tiles_n, n_tiles_m;   // persistent tile walk: tile = (z * n_tiles_m + m) * n_tiles_n + n
     int w_dy, w_dx, w_sy, w_sx;      // X-box origin = (y0*w_sy + w_dy, x0*w_sx + w_dx)  (per launch = per tap)
     // ---- epilogue -----------------------------------------------------------------------------
     int Mo_rows;                     // wgrad: number of valid output rows (Cout)
@@ -56,17 +57,23 @@ struct TcParams {
     float* out;
 };
 
-// SPLIT = error-compensated "3xTF32": the four epilogue warps double as splitter warps during the main loop; for
-// every landed stage they write lo = x - trunc_tf32(x) of both tiles next to the raw tiles, and the MMA warp issues
-// A*B + A_lo*B + A*B_lo (the tensor core truncates the raw fp32 bits itself), which restores ~fp32 accuracy.
+// Persistent, warp-specialised kernel.  Each CTA walks tiles  tile = blockIdx.x + i * gridDim.x  and keeps
+//   warp 0          TMA producer (smem ring of STAGES stages, full/empty mbarriers)
+//   warp 1          TMEM allocator + single-thread tcgen05.mma issuer; TWO accumulators in TMEM so that
+//   last 4 warps    the epilogue of tile i (tcgen05.ld -> fused bias/residual/ReLU/mask/row-scale -> global)
+//                   overlaps the main loop of tile i+1 (tmem_full / tmem_empty mbarriers)
+//   warps 2-5       (SPLIT only) splitter warps: error-compensated "3xTF32".  For every landed stage they write
+//                   lo = x - trunc_tf32(x) of both tiles next to the raw tiles; the MMA warp then issues
+//                   A*B + A_lo*B + A*B_lo (the tensor core truncates the raw fp32 bits itself) = ~fp32 accuracy.
 template <int BN, int STAGES, int MODE /*0 fprop/dgrad, 1 wgrad*/, bool B_MN, bool SPLIT>
-__global__ void __launch_bounds__(kThreadsTC)
+__global__ void __launch_bounds__(SPLIT ? 320 : 192)
 tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const __grid_constant__ TcParams p) {
     constexpr bool A_MN = (MODE == 1);
     constexpr int kTileBBytes = BN * 128;
     constexpr int kRawBytes = kTileABytes + kTileBBytes;          // what TMA delivers per stage
     constexpr int kStageBytes = SPLIT ? 2 * kRawBytes : kRawBytes;  // + the lo tiles
+    constexpr int kEpiWarp0 = SPLIT ? 6 : 2;                        // first epilogue warp
     static_assert(!(MODE == 1) || B_MN, "wgrad reads both operands MN-major");
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -74,30 +81,36 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* split_bar = empty_bar + STAGES;                     // splitter warps -> MMA (SPLIT only)
-    uint64_t* tmem_full = split_bar + STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = split_bar + STAGES;                     // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    // ---- tile coordinates ------------------------------------------------------------------------
-    const int n0 = blockIdx.x * BN;          // output-column tile
-    int img = 0, y0 = 0, x0 = 0, m0 = 0, red_begin = 0, red_end = 0, total_iters = 0;
-    if constexpr (MODE == 0) {
-        int t = blockIdx.y;
-        const int per_img = p.tiles_x * p.tiles_y;
-        img = t / per_img;
-        t -= img * per_img;
-        y0 = (t / p.tiles_x) * p.th;
-        x0 = (t % p.tiles_x) * p.tw;
-        total_iters = p.ntaps * p.cblocks;
-    } else {
-        m0 = blockIdx.y * BM;                // output rows = Cout
-        const int total_red = p.n_img * p.rtiles_x * p.rtiles_y;
-        red_begin = blockIdx.z * p.red_per_split;
-        red_end = min(total_red, red_begin + p.red_per_split);
-        total_iters = max(0, red_end - red_begin);
-    }
+    // ---- tile decode (identical in every role) -----------------------------------------------------
+    struct Tile { int n0, img, y0, x0, m0, red_begin, iters; };
+    auto decode = [&](int tix) {
+        Tile t;
+        t.n0 = (tix % p.n_tiles_n) * BN;
+        int r = tix / p.n_tiles_n;
+        t.img = t.y0 = t.x0 = t.m0 = t.red_begin = 0;
+        if constexpr (MODE == 0) {
+            const int per_img = p.tiles_x * p.tiles_y;
+            t.img = r / per_img;
+            r -= t.img * per_img;
+            t.y0 = (r / p.tiles_x) * p.th;
+            t.x0 = (r % p.tiles_x) * p.tw;
+            t.iters = p.ntaps * p.cblocks;
+        } else {
+            t.m0 = (r % p.n_tiles_m) * BM;
+            const int z = r / p.n_tiles_m;
+            const int total_red = p.n_img * p.rtiles_x * p.rtiles_y;
+            t.red_begin = z * p.red_per_split;
+            t.iters = max(0, min(total_red, t.red_begin + p.red_per_split) - t.red_begin);
+        }
+        return t;
+    };
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&mapA);
@@ -107,10 +120,13 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             mbar_init(&empty_bar[s], 1);
             mbar_init(&split_bar[s], 4);                          // one arrival per splitter warp
         }
-        mbar_init(tmem_full, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full[a], 1);
+            mbar_init(&tmem_empty[a], 4);                         // one arrival per epilogue warp
+        }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<BN>(tmem_slot);
+    if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -119,39 +135,43 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     if (warp == 0) {
         // ================================ TMA producer =============================================
         if (elect_one()) {
-            for (int it = 0; it < total_iters; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                uint8_t* a_dst = smem + s * kStageBytes;
-                uint8_t* b_dst = a_dst + kTileABytes;
-                mbar_arrive_expect_tx(&full_bar[s], kRawBytes);
-                if constexpr (MODE == 0) {
-                    const int tap = it / p.cblocks;
-                    const int cb = it - tap * p.cblocks;
-                    tma_load_4d(a_dst, &mapA, &full_bar[s], cb * BK, x0 * p.in_sx + p.tap_dx[tap],
-                                y0 * p.in_sy + p.tap_dy[tap], img);
-                    if constexpr (!B_MN) {
-                        tma_load_3d(b_dst, &mapB, &full_bar[s], cb * BK, n0, p.tap_w[tap]);
+            int git = 0;                                          // ring position, continues across tiles
+            for (int tix = blockIdx.x; tix < p.total_tiles; tix += gridDim.x) {
+                const Tile t = decode(tix);
+                for (int it = 0; it < t.iters; ++it, ++git) {
+                    const int s = git % STAGES;
+                    const uint32_t ph = (git / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* a_dst = smem + s * kStageBytes;
+                    uint8_t* b_dst = a_dst + kTileABytes;
+                    mbar_arrive_expect_tx(&full_bar[s], kRawBytes);
+                    if constexpr (MODE == 0) {
+                        const int tap = it / p.cblocks;
+                        const int cb = it - tap * p.cblocks;
+                        tma_load_4d(a_dst, &mapA, &full_bar[s], cb * BK, t.x0 * p.in_sx + p.tap_dx[tap],
+                                    t.y0 * p.in_sy + p.tap_dy[tap], t.img);
+                        if constexpr (!B_MN) {
+                            tma_load_3d(b_dst, &mapB, &full_bar[s], cb * BK, t.n0, p.tap_w[tap]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BN / 32; ++j)
+                                tma_load_3d(b_dst + j * kChunkBytes, &mapB, &full_bar[s], t.n0 + j * 32, cb * BK, p.tap_w[tap]);
+                        }
                     } else {
+                        int r = t.red_begin + it;
+                        const int per_img = p.rtiles_x * p.rtiles_y;
+                        const int ri = r / per_img;
+                        r -= ri * per_img;
+                        const int ry = (r / p.rtiles_x) * p.rth;
+                        const int rx = (r % p.rtiles_x) * p.rtw;
+#pragma unroll
+                        for (int j = 0; j < BM / 32; ++j)
+                            tma_load_4d(a_dst + j * kChunkBytes, &mapA, &full_bar[s], t.m0 + j * 32, rx, ry, ri);
 #pragma unroll
                         for (int j = 0; j < BN / 32; ++j)
-                            tma_load_3d(b_dst + j * kChunkBytes, &mapB, &full_bar[s], n0 + j * 32, cb * BK, p.tap_w[tap]);
+                            tma_load_4d(b_dst + j * kChunkBytes, &mapB, &full_bar[s], t.n0 + j * 32, rx * p.w_sx + p.w_dx,
+                                        ry * p.w_sy + p.w_dy, ri);
                     }
-                } else {
-                    int r = red_begin + it;
-                    const int per_img = p.rtiles_x * p.rtiles_y;
-                    const int ri = r / per_img;
-                    r -= ri * per_img;
-                    const int ry = (r / p.rtiles_x) * p.rth;
-                    const int rx = (r % p.rtiles_x) * p.rtw;
-#pragma unroll
-                    for (int j = 0; j < BM / 32; ++j)
-                        tma_load_4d(a_dst + j * kChunkBytes, &mapA, &full_bar[s], m0 + j * 32, rx, ry, ri);
-#pragma unroll
-                    for (int j = 0; j < BN / 32; ++j)
-                        tma_load_4d(b_dst + j * kChunkBytes, &mapB, &full_bar[s], n0 + j * 32, rx * p.w_sx + p.w_dx,
-                                    ry * p.w_sy + p.w_dy, ri);
                 }
             }
         }
@@ -159,47 +179,59 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         // ================================ MMA issuer ==============================================
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_tf32(BM, BN, A_MN, B_MN);
-            for (int it = 0; it < total_iters; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(SPLIT ? &split_bar[s] : &full_bar[s], ph);
+            int git = 0, lt = 0;                                  // lt counts tiles that have a main loop
+            for (int tix = blockIdx.x; tix < p.total_tiles; tix += gridDim.x) {
+                const Tile t = decode(tix);
+                if (t.iters == 0) continue;
+                const int slot = lt & 1;
+                mbar_wait(&tmem_empty[slot], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
-                const uint32_t b_addr = a_addr + kTileABytes;
+                const uint32_t tacc = tmem_base + slot * BN;
+                for (int it = 0; it < t.iters; ++it, ++git) {
+                    const int s = git % STAGES;
+                    const uint32_t ph = (git / STAGES) & 1;
+                    mbar_wait(SPLIT ? &split_bar[s] : &full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
+                    const uint32_t b_addr = a_addr + kTileABytes;
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k) {
-                    // K-major (SWIZZLE_128B): 8 fp32 = 32 B further along the 128-B row; 8-row groups 1024 B apart (SBO).
-                    // MN-major (128B swizzle, 32-B atoms, 4-row period): 8 reduction rows = 1024 B further per k-step;
-                    // 4-row groups 512 B apart (SBO); 32-wide MN chunks 4096 B apart (LBO).
-                    const uint32_t ao = A_MN ? k * 1024 : k * 32, bo = B_MN ? k * 1024 : k * 32;
-                    const uint64_t adesc = A_MN ? make_smem_desc(a_addr + ao, kChunkBytes, 512, 1) : make_smem_desc(a_addr + ao, 16, 1024, 2);
-                    const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + bo, kChunkBytes, 512, 1) : make_smem_desc(b_addr + bo, 16, 1024, 2);
-                    umma_tf32(tmem_base, adesc, bdesc, idesc, (it > 0) || (k > 0));
-                    if constexpr (SPLIT) {
-                        const uint64_t alo = A_MN ? make_smem_desc(a_addr + kRawBytes + ao, kChunkBytes, 512, 1)
-                                                  : make_smem_desc(a_addr + kRawBytes + ao, 16, 1024, 2);
-                        const uint64_t blo = B_MN ? make_smem_desc(b_addr + kRawBytes + bo, kChunkBytes, 512, 1)
-                                                  : make_smem_desc(b_addr + kRawBytes + bo, 16, 1024, 2);
-                        umma_tf32(tmem_base, alo, bdesc, idesc, true);
-                        umma_tf32(tmem_base, adesc, blo, idesc, true);
+                    for (int k = 0; k < BK / 8; ++k) {
+                        // K-major (SWIZZLE_128B): 8 fp32 = 32 B further along the 128-B row; 8-row groups 1024 B apart (SBO).
+                        // MN-major (128B swizzle, 32-B atoms, 4-row period): 8 reduction rows = 1024 B further per k-step;
+                        // 4-row groups 512 B apart (SBO); 32-wide MN chunks 4096 B apart (LBO).
+                        const uint32_t ao = A_MN ? k * 1024 : k * 32, bo = B_MN ? k * 1024 : k * 32;
+                        const uint64_t adesc = A_MN ? make_smem_desc(a_addr + ao, kChunkBytes, 512, 1) : make_smem_desc(a_addr + ao, 16, 1024, 2);
+                        const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + bo, kChunkBytes, 512, 1) : make_smem_desc(b_addr + bo, 16, 1024, 2);
+                        umma_tf32(tacc, adesc, bdesc, idesc, (it > 0) || (k > 0));
+                        if constexpr (SPLIT) {
+                            const uint64_t alo = A_MN ? make_smem_desc(a_addr + kRawBytes + ao, kChunkBytes, 512, 1)
+                                                      : make_smem_desc(a_addr + kRawBytes + ao, 16, 1024, 2);
+                            const uint64_t blo = B_MN ? make_smem_desc(b_addr + kRawBytes + bo, kChunkBytes, 512, 1)
+                                                      : make_smem_desc(b_addr + kRawBytes + bo, 16, 1024, 2);
+                            umma_tf32(tacc, alo, bdesc, idesc, true);
+                            umma_tf32(tacc, adesc, blo, idesc, true);
+                        }
                     }
+                    umma_commit(&empty_bar[s]);                   // frees the smem stage when these MMAs retire
                 }
-                umma_commit(&empty_bar[s]);    // frees the smem stage when these MMAs retire
+                umma_commit(&tmem_full[slot]);                    // accumulator complete
+                ++lt;
             }
-            umma_commit(tmem_full);            // accumulator complete
         }
-    } else {
-        // ================================ splitter (SPLIT) + epilogue ================================
-        if constexpr (SPLIT) {
-            const int t = threadIdx.x - 64;    // 0..127
-            for (int it = 0; it < total_iters; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
+    } else if (SPLIT && warp < kEpiWarp0) {
+        // ================================ splitter warps (3xTF32) ===================================
+        const int tid = threadIdx.x - 64;                         // 0..127
+        int git = 0;
+        for (int tix = blockIdx.x; tix < p.total_tiles; tix += gridDim.x) {
+            const Tile t = decode(tix);
+            for (int it = 0; it < t.iters; ++it, ++git) {
+                const int s = git % STAGES;
+                const uint32_t ph = (git / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
                 const uint4* raw = reinterpret_cast<const uint4*>(smem + s * kStageBytes);
                 float4* lo = reinterpret_cast<float4*>(smem + s * kStageBytes + kRawBytes);
 #pragma unroll 4
-                for (int i = t; i < kRawBytes / 16; i += 128) {
+                for (int i = tid; i < kRawBytes / 16; i += 128) {
                     const uint4 r = raw[i];
                     float4 l;
                     l.x = __uint_as_float(r.x) - __uint_as_float(r.x & 0xFFFFE000u);
@@ -213,82 +245,95 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 if (lane == 0) mbar_arrive(&split_bar[s]);
             }
         }
+    } else if (warp >= kEpiWarp0) {
+        // ================================ epilogue warps ===========================================
         const int q = warp & 3;                // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;
-        bool row_ok;
-        size_t out_row;                        // element offset of (row, column 0) in out / residual / mask
-        float rscale = 1.f;
-        if constexpr (MODE == 0) {
-            const int ly = row / p.tw, lx = row - ly * p.tw;
-            const int y = y0 + ly, x = x0 + lx;
-            row_ok = (y < p.Ho) && (x < p.Wo);
-            const int oy = y * p.out_sy + p.out_oy, ox = x * p.out_sx + p.out_ox;
-            out_row = (((size_t)img * p.out_H + oy) * p.out_W + ox) * (size_t)p.ldo;
-        } else {
-            row_ok = (m0 + row) < p.Mo_rows;
-            out_row = (size_t)(m0 + row) * p.ldo;
-            if (row_ok && p.rowscale) rscale = p.rowscale[m0 + row];
-        }
-        if (total_iters > 0) {
-            mbar_wait(tmem_full, 0);
-            tc_fence_after();
-        }
-        const uint32_t taddr_row = tmem_base + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            if (n0 + c0 >= p.No) break;        // uniform across the CTA
-            uint32_t r[32];
-            if (total_iters > 0) {
-                tmem_ld_32x32(taddr_row + c0, r);
-                tmem_ld_wait();
+        int lt = 0;
+        for (int tix = blockIdx.x; tix < p.total_tiles; tix += gridDim.x) {
+            const Tile t = decode(tix);
+            bool row_ok;
+            size_t out_row;                    // element offset of (row, column 0) in out / residual / mask
+            float rscale = 1.f;
+            if constexpr (MODE == 0) {
+                const int ly = row / p.tw, lx = row - ly * p.tw;
+                const int y = t.y0 + ly, x = t.x0 + lx;
+                row_ok = (y < p.Ho) && (x < p.Wo);
+                const int oy = y * p.out_sy + p.out_oy, ox = x * p.out_sx + p.out_ox;
+                out_row = (((size_t)t.img * p.out_H + oy) * p.out_W + ox) * (size_t)p.ldo;
             } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = 0u;
+                row_ok = (t.m0 + row) < p.Mo_rows;
+                out_row = (size_t)(t.m0 + row) * p.ldo;
+                if (row_ok && p.rowscale) rscale = p.rowscale[t.m0 + row];
             }
-            if (!row_ok) continue;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const int n = n0 + c0 + j;
-                if (n >= p.No) break;
-                float v[4] = {__uint_as_float(r[j]) * rscale, __uint_as_float(r[j + 1]) * rscale,
-                              __uint_as_float(r[j + 2]) * rscale, __uint_as_float(r[j + 3]) * rscale};
-                const size_t o = out_row + n;
-                if (n + 3 < p.No) {
-                    if (p.bias) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                        v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-                    }
-                    if (p.residual) {
-                        const float4 b = *reinterpret_cast<const float4*>(p.residual + o);
-                        v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-                    }
-                    if (p.relu) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
-                    }
-                    if (p.relu_mask) {
-                        const float4 b = *reinterpret_cast<const float4*>(p.relu_mask + o);
-                        v[0] = b.x > 0.f ? v[0] : 0.f; v[1] = b.y > 0.f ? v[1] : 0.f;
-                        v[2] = b.z > 0.f ? v[2] : 0.f; v[3] = b.w > 0.f ? v[3] : 0.f;
-                    }
-                    if (p.round_out) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) v[e] = round_tf32(v[e]);
-                    }
-                    if (p.atomic_out) red_add_v4_f32(p.out + o, v[0], v[1], v[2], v[3]);
-                    else *reinterpret_cast<float4*>(p.out + o) = make_float4(v[0], v[1], v[2], v[3]);
+            const int slot = lt & 1;
+            if (t.iters > 0) {
+                mbar_wait(&tmem_full[slot], (lt >> 1) & 1);
+                tc_fence_after();
+            }
+            const uint32_t taddr_row = tmem_base + slot * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (t.n0 + c0 >= p.No) break;  // uniform across the CTA
+                uint32_t r[32];
+                if (t.iters > 0) {
+                    tmem_ld_32x32(taddr_row + c0, r);
+                    tmem_ld_wait();
                 } else {
-                    for (int e = 0; e < 4 && n + e < p.No; ++e) {
-                        float x = v[e];
-                        if (p.bias) x += p.bias[n + e];
-                        if (p.residual) x += p.residual[o + e];
-                        if (p.relu) x = fmaxf(x, 0.f);
-                        if (p.relu_mask) x = p.relu_mask[o + e] > 0.f ? x : 0.f;
-                        if (p.round_out) x = round_tf32(x);
-                        if (p.atomic_out) atomicAdd(p.out + o + e, x);
-                        else p.out[o + e] = x;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = 0u;
+                }
+                if (!row_ok) continue;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = t.n0 + c0 + j;
+                    if (n >= p.No) break;
+                    float v[4] = {__uint_as_float(r[j]) * rscale, __uint_as_float(r[j + 1]) * rscale,
+                                  __uint_as_float(r[j + 2]) * rscale, __uint_as_float(r[j + 3]) * rscale};
+                    const size_t o = out_row + n;
+                    if (n + 3 < p.No) {
+                        if (p.bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+                        }
+                        if (p.residual) {
+                            const float4 b = *reinterpret_cast<const float4*>(p.residual + o);
+                            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+                        }
+                        if (p.relu_mask) {
+                            const float4 b = *reinterpret_cast<const float4*>(p.relu_mask + o);
+                            v[0] = b.x > 0.f ? v[0] : 0.f; v[1] = b.y > 0.f ? v[1] : 0.f;
+                            v[2] = b.z > 0.f ? v[2] : 0.f; v[3] = b.w > 0.f ? v[3] : 0.f;
+                        }
+                        if (p.round_out) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) v[e] = round_tf32(v[e]);
+                        }
+                        if (p.atomic_out) red_add_v4_f32(p.out + o, v[0], v[1], v[2], v[3]);
+                        else *reinterpret_cast<float4*>(p.out + o) = make_float4(v[0], v[1], v[2], v[3]);
+                    } else {
+                        for (int e = 0; e < 4 && n + e < p.No; ++e) {
+                            float x = v[e];
+                            if (p.bias) x += p.bias[n + e];
+                            if (p.residual) x += p.residual[o + e];
+                            if (p.relu) x = fmaxf(x, 0.f);
+                            if (p.relu_mask) x = p.relu_mask[o + e] > 0.f ? x : 0.f;
+                            if (p.round_out) x = round_tf32(x);
+                            if (p.atomic_out) atomicAdd(p.out + o + e, x);
+                            else p.out[o + e] = x;
+                        }
                     }
                 }
+            }
+            if (t.iters > 0) {
+                tc_fence_before();             // TMEM reads of this warp are done: hand the accumulator back
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+                ++lt;
             }
         }
     }
@@ -296,7 +341,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<BN>(tmem_base);
+        tmem_dealloc<2 * BN>(tmem_base);
     }
 }
 
@@ -347,9 +392,21 @@ int make_map(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, 
 
 int g_precision = 1;   // 0 = single-pass TF32 (operands rounded to nearest), 1 = error-compensated 3xTF32 (default)
 
+int num_sms_tc() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    }
+    return sms;
+}
+
+// `grid` carries the logical tile counts (x = column tiles, y = row tiles, z = split-K slices); the kernel is
+// launched persistent with min(total_tiles, SMs * resident CTAs) CTAs.
 template <int BN, int STAGES, int MODE, bool B_MN, bool SPLIT>
-int launch_tc(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, dim3 grid, cudaStream_t stream) {
+int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, dim3 grid, cudaStream_t stream) {
     constexpr int smem = STAGES * (SPLIT ? 2 : 1) * (kTileABytes + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
+    constexpr int threads = SPLIT ? 320 : 192;
     static bool configured = false;
     auto kern = tc_conv_gemm_kernel<BN, STAGES, MODE, B_MN, SPLIT>;
     if (!configured) {
@@ -357,7 +414,14 @@ int launch_tc(const CUtensorMap& a, const CUtensorMap& b, const TcParams& p, dim
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    kern<<<grid, kThreadsTC, smem, stream>>>(a, b, p);
+    p.n_tiles_n = (int)grid.x;
+    p.n_tiles_m = (int)grid.y;
+    p.total_tiles = (int)(grid.x * grid.y * grid.z);
+    const int resident = (smem <= 110 * 1024 && 2 * BN * 2 <= 512) ? 2 : 1;   // smem and TMEM (2*BN columns per CTA)
+    int ctas = num_sms_tc() * resident;
+    if (ctas > p.total_tiles) ctas = p.total_tiles;
+    if (ctas < 1) return 0;
+    kern<<<ctas, threads, smem, stream>>>(a, b, p);
     return (int)cudaGetLastError();
 }
 
