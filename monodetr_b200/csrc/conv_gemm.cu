@@ -33,6 +33,8 @@ constexpr int kTileABytes = BM * 128;  // 16 KiB
 constexpr int kChunkBytes = 32 * 128;  // one MN-major chunk: 32 reduction rows x 128 B
 constexpr int kThreadsTC = 192;
 constexpr int kMaxTaps = 9;
+constexpr int kPatchLd = 36;             // padded row stride (floats) of an epilogue warp's 32x32 transpose patch
+constexpr int kPatchBytes = 4 * 32 * kPatchLd * 4;   // four epilogue warps
 
 struct TcParams {
     // ---- fprop / dgrad: decomposition of the M dimension into th x tw pixel rectangles ----------
@@ -247,24 +249,36 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
     } else if (warp >= kEpiWarp0) {
         // ================================ epilogue warps ===========================================
+        // TMEM gives thread `lane` the accumulator ROW q*32+lane (32 consecutive columns per tcgen05.ld).  Writing
+        // that straight out would touch 32 different cache lines per store instruction, so every 32x32 block is
+        // transposed through a private padded smem patch: afterwards 8 lanes x float4 cover one row's 128 bytes and
+        // a warp instruction moves 4 full lines -- residual / mask reads use the same coalesced pattern.
         const int q = warp & 3;                // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;
+        float* patch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256) + (warp - kEpiWarp0) * (32 * kPatchLd);
+        const int r4 = lane >> 3, c4 = lane & 7;
         int lt = 0;
         for (int tix = blockIdx.x; tix < p.total_tiles; tix += gridDim.x) {
             const Tile t = decode(tix);
-            bool row_ok;
-            size_t out_row;                    // element offset of (row, column 0) in out / residual / mask
-            float rscale = 1.f;
-            if constexpr (MODE == 0) {
-                const int ly = row / p.tw, lx = row - ly * p.tw;
-                const int y = t.y0 + ly, x = t.x0 + lx;
-                row_ok = (y < p.Ho) && (x < p.Wo);
-                const int oy = y * p.out_sy + p.out_oy, ox = x * p.out_sx + p.out_ox;
-                out_row = (((size_t)t.img * p.out_H + oy) * p.out_W + ox) * (size_t)p.ldo;
-            } else {
-                row_ok = (t.m0 + row) < p.Mo_rows;
-                out_row = (size_t)(t.m0 + row) * p.ldo;
-                if (row_ok && p.rowscale) rscale = p.rowscale[t.m0 + row];
+            size_t roff[8];                    // element offset of (row, column 0) for the 8 rows this lane stores
+            float rsc[8];
+            uint32_t rok = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = q * 32 + i * 4 + r4;
+                rsc[i] = 1.f;
+                if constexpr (MODE == 0) {
+                    const int ly = row / p.tw, lx = row - ly * p.tw;
+                    const int y = t.y0 + ly, x = t.x0 + lx;
+                    if ((y < p.Ho) && (x < p.Wo)) rok |= 1u << i;
+                    const int oy = y * p.out_sy + p.out_oy, ox = x * p.out_sx + p.out_ox;
+                    roff[i] = (((size_t)t.img * p.out_H + oy) * p.out_W + ox) * (size_t)p.ldo;
+                } else {
+                    if ((t.m0 + row) < p.Mo_rows) {
+                        rok |= 1u << i;
+                        if (p.rowscale) rsc[i] = p.rowscale[t.m0 + row];
+                    }
+                    roff[i] = (size_t)(t.m0 + row) * p.ldo;
+                }
             }
             const int slot = lt & 1;
             if (t.iters > 0) {
@@ -283,19 +297,22 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = 0u;
                 }
-                if (!row_ok) continue;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int n = t.n0 + c0 + j;
-                    if (n >= p.No) break;
-                    float v[4] = {__uint_as_float(r[j]) * rscale, __uint_as_float(r[j + 1]) * rscale,
-                                  __uint_as_float(r[j + 2]) * rscale, __uint_as_float(r[j + 3]) * rscale};
-                    const size_t o = out_row + n;
-                    if (n + 3 < p.No) {
-                        if (p.bias) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-                        }
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(patch + lane * kPatchLd + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                __syncwarp();
+                const int n = t.n0 + c0 + c4 * 4;
+                const bool vec = (n + 3 < p.No);
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias && vec) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (!((rok >> i) & 1u) || n >= p.No) continue;
+                    const float4 a = *reinterpret_cast<const float4*>(patch + (i * 4 + r4) * kPatchLd + c4 * 4);
+                    float v[4] = {a.x * rsc[i], a.y * rsc[i], a.z * rsc[i], a.w * rsc[i]};
+                    const size_t o = roff[i] + n;
+                    if (vec) {
+                        v[0] += bias4.x; v[1] += bias4.y; v[2] += bias4.z; v[3] += bias4.w;
                         if (p.residual) {
                             const float4 b = *reinterpret_cast<const float4*>(p.residual + o);
                             v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
@@ -328,6 +345,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         }
                     }
                 }
+                __syncwarp();                  // the patch is rewritten by the next chunk
             }
             if (t.iters > 0) {
                 tc_fence_before();             // TMEM reads of this warp are done: hand the accumulator back
@@ -405,7 +423,7 @@ int num_sms_tc() {
 // launched persistent with min(total_tiles, SMs * resident CTAs) CTAs.
 template <int BN, int STAGES, int MODE, bool B_MN, bool SPLIT>
 int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, dim3 grid, cudaStream_t stream) {
-    constexpr int smem = STAGES * (SPLIT ? 2 : 1) * (kTileABytes + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/;
+    constexpr int smem = STAGES * (SPLIT ? 2 : 1) * (kTileABytes + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/ + kPatchBytes;
     constexpr int threads = SPLIT ? 320 : 192;
     static bool configured = false;
     auto kern = tc_conv_gemm_kernel<BN, STAGES, MODE, B_MN, SPLIT>;
@@ -417,7 +435,7 @@ int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, dim3 grid,
     p.n_tiles_n = (int)grid.x;
     p.n_tiles_m = (int)grid.y;
     p.total_tiles = (int)(grid.x * grid.y * grid.z);
-    const int resident = (smem <= 110 * 1024 && 2 * BN * 2 <= 512) ? 2 : 1;   // smem and TMEM (2*BN columns per CTA)
+    const int resident = (smem <= 112 * 1024 && 2 * BN * 2 <= 512) ? 2 : 1;   // smem and TMEM (2*BN columns per CTA)
     int ctas = num_sms_tc() * resident;
     if (ctas > p.total_tiles) ctas = p.total_tiles;
     if (ctas < 1) return 0;
@@ -498,7 +516,7 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
         if (rc) return rc;
     }
     const bool wide = (g_precision == 0) && (Cout >= 256) && ((long long)B * p.tiles_x * p.tiles_y * (Cout / 256) >= 120);
-    const int bn = wide ? 256 : 128;
+    const int bn = wide ? 256 : (Cout <= 64 ? 64 : 128);
     {   // B: packed weights as (Cin, Cout, taps), box (32, BN, 1)
         uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
         uint64_t str[3] = {1, (uint64_t)Cin, (uint64_t)Cout * Cin};
@@ -507,9 +525,11 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
         if (rc) return rc;
     }
     dim3 grid((Cout + bn - 1) / bn, B * p.tiles_x * p.tiles_y, 1);
+    if (bn == 64) return (g_precision == 1) ? launch_tc<64, 4, 0, false, true>(ma, mb, p, grid, stream)
+                                            : launch_tc<64, 6, 0, false, false>(ma, mb, p, grid, stream);
     if (g_precision == 1) return launch_tc<128, 3, 0, false, true>(ma, mb, p, grid, stream);
     if (wide) return launch_tc<256, 4, 0, false, false>(ma, mb, p, grid, stream);
-    return launch_tc<128, 3, 0, false, false>(ma, mb, p, grid, stream);
+    return launch_tc<128, 5, 0, false, false>(ma, mb, p, grid, stream);
 }
 
 // dx[B,H,W,Cin] = (conv_transpose(dy[B,Ho,Wo,Cout], w_packed) + residual) * (relu_mask > 0)
@@ -572,7 +592,7 @@ int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* re
                 p.ntaps = 0;
             }
             rc = (g_precision == 1) ? launch_tc<128, 3, 0, true, true>(ma, mb, p, grid, stream)
-                                    : launch_tc<128, 3, 0, true, false>(ma, mb, p, grid, stream);
+                                    : launch_tc<128, 5, 0, true, false>(ma, mb, p, grid, stream);
             if (rc) return rc;
         }
     return 0;
@@ -633,7 +653,7 @@ int mdb_conv2d_wgrad_f32(const float* dy, const float* x, const float* rowscale,
         dim3 grid((Cin + bn - 1) / bn, (Cout + BM - 1) / BM, splits);
         rc = (g_precision == 1) ? launch_tc<128, 3, 1, true, true>(ma, mb, p, grid, stream)
              : (bn == 256)      ? launch_tc<256, 4, 1, true, false>(ma, mb, p, grid, stream)
-                                : launch_tc<128, 3, 1, true, false>(ma, mb, p, grid, stream);
+                                : launch_tc<128, 5, 1, true, false>(ma, mb, p, grid, stream);
         if (rc) return rc;
     }
     return 0;
