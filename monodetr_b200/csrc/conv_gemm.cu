@@ -289,6 +289,19 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 if (t.n0 + c0 >= p.No) break;  // uniform across the CTA
+                // Issue every global read of this chunk (residual, ReLU mask, bias) BEFORE waiting on TMEM, through the
+                // read-only path, so their latency overlaps instead of serialising 32 dependent loads per thread.
+                const int n = t.n0 + c0 + c4 * 4;
+                const bool vec = (n + 3 < p.No);
+                float4 res[8], msk[8];
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias && vec) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const bool ok = ((rok >> i) & 1u) && vec;
+                    res[i] = (p.residual && ok) ? __ldg(reinterpret_cast<const float4*>(p.residual + roff[i] + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    msk[i] = (p.relu_mask && ok) ? __ldg(reinterpret_cast<const float4*>(p.relu_mask + roff[i] + n)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                }
                 uint32_t r[32];
                 if (t.iters > 0) {
                     tmem_ld_32x32(taddr_row + c0, r);
@@ -301,10 +314,6 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<uint4*>(patch + lane * kPatchLd + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                 __syncwarp();
-                const int n = t.n0 + c0 + c4 * 4;
-                const bool vec = (n + 3 < p.No);
-                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias && vec) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     if (!((rok >> i) & 1u) || n >= p.No) continue;
@@ -312,20 +321,13 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     float v[4] = {a.x * rsc[i], a.y * rsc[i], a.z * rsc[i], a.w * rsc[i]};
                     const size_t o = roff[i] + n;
                     if (vec) {
-                        v[0] += bias4.x; v[1] += bias4.y; v[2] += bias4.z; v[3] += bias4.w;
-                        if (p.residual) {
-                            const float4 b = *reinterpret_cast<const float4*>(p.residual + o);
-                            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-                        }
+                        v[0] += bias4.x + res[i].x; v[1] += bias4.y + res[i].y; v[2] += bias4.z + res[i].z; v[3] += bias4.w + res[i].w;
                         if (p.relu) {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
                         }
-                        if (p.relu_mask) {
-                            const float4 b = *reinterpret_cast<const float4*>(p.relu_mask + o);
-                            v[0] = b.x > 0.f ? v[0] : 0.f; v[1] = b.y > 0.f ? v[1] : 0.f;
-                            v[2] = b.z > 0.f ? v[2] : 0.f; v[3] = b.w > 0.f ? v[3] : 0.f;
-                        }
+                        v[0] = msk[i].x > 0.f ? v[0] : 0.f; v[1] = msk[i].y > 0.f ? v[1] : 0.f;
+                        v[2] = msk[i].z > 0.f ? v[2] : 0.f; v[3] = msk[i].w > 0.f ? v[3] : 0.f;
                         if (p.round_out) {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) v[e] = round_tf32(v[e]);
