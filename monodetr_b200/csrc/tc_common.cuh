@@ -47,18 +47,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trap (launch failure) after ~2 s instead of a hung GPU.
-__device__ __forceinline__ uint64_t global_ns() {
+// Bounded wait: a protocol bug becomes a trap (launch failure) after ~2 s instead of a hung GPU.  The timer is read
+// in a NOINLINE slow path once per 16384 failed polls: reading %globaltimer in the poll loop itself (which the compiler
+// happily if-converts into every iteration) adds its latency to EVERY producer/consumer hand-off of the pipeline.
+__device__ __noinline__ void mbar_slow_path(uint64_t& t0) {
     uint64_t t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
+    if (t0 == 0) t0 = t;
+    else if (t - t0 > 2000000000ull) __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const uint64_t t0 = global_ns();
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 1023u) == 0 && global_ns() - t0 > 2000000000ull) __trap();
+        if (++spins == 16384u) {
+            spins = 0;
+            mbar_slow_path(t0);
+        }
     }
 }
 
