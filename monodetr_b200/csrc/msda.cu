@@ -49,15 +49,20 @@ __device__ __forceinline__ double floor_t(double a) { return floor(a); }
 // ------------------------------------------------------------------------------------------------
 // Fast forward: LPU lanes per unit, D = 4*LPU, P = 4.
 // ------------------------------------------------------------------------------------------------
-template <int LPU>
+// Work distribution: every CTA owns one CONTIGUOUS range of units (= consecutive queries; in the encoder that is a
+// strip of horizontally adjacent pixels), and its 8 warps walk it side by side, so that the bilinear footprints of
+// neighbouring queries are re-read from the SM's L1 instead of L2 (an interleaved grid-stride walk spreads a strip over
+// all SMs and gets ~35 % L1 hits; the contiguous walk reuses a line across ~8 neighbouring queries).
+template <int LPU, int LT /*compile-time level count, 0 = runtime*/>
 __global__ void __launch_bounds__(kThreads)
 msda_fwd_vec_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
-                    const float* __restrict__ attn, int S, int M, int L, int Lq, long long n_units,
-                    float* __restrict__ out) {
+                    const float* __restrict__ attn, int S, int M, int L_rt, int Lq, long long n_units,
+                    long long units_per_block, float* __restrict__ out) {
     constexpr int D = 4 * LPU;
     constexpr int UPW = 32 / LPU;
     constexpr int P = 4;
+    const int L = LT ? LT : L_rt;
     __shared__ LevelInfo lv;
     if (threadIdx.x < L) {
         lv.H[threadIdx.x] = (int)shapes[2 * threadIdx.x];
@@ -69,20 +74,24 @@ msda_fwd_vec_kernel(const float* __restrict__ value, const int64_t* __restrict__
     const int lane = threadIdx.x & 31;
     const int sub = lane / LPU;
     const int cl = lane % LPU;
-    const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const long long nwarps = (long long)gridDim.x * (kThreads / 32);
+    const int wib = threadIdx.x >> 5;
     const int pix = M * D;  // floats between horizontally adjacent pixels
+    const long long u_begin = (long long)blockIdx.x * units_per_block;
+    const long long u_end = min(n_units, u_begin + units_per_block);
 
-    for (long long unit = warp * UPW + sub; unit < n_units; unit += nwarps * UPW) {
+    for (long long unit = u_begin + wib * UPW + sub; unit < u_end; unit += (kThreads / 32) * UPW) {
         const int m = (int)(unit % M);
-        const long long b = unit / ((long long)Lq * M);
+        const int b = (int)(unit / ((long long)Lq * M));
         const float* vb = value + ((size_t)b * S * M + m) * D + cl * 4;
         const float* lp = loc + (size_t)unit * L * P * 2;
         const float* ap = attn + (size_t)unit * L * P;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 
-        for (int l = 0; l < L; ++l) {
+#pragma unroll
+        for (int l = 0; l < (LT ? LT : kMaxLevels); ++l) {
+            if (!LT && l >= L) break;
             const int H = lv.H[l], W = lv.W[l];
+            const float fW = (float)W, fH = (float)H;
             const float* vl = vb + (size_t)lv.start[l] * pix;
             const float4 xy01 = ldg4(lp + l * 8);
             const float4 xy23 = ldg4(lp + l * 8 + 4);
@@ -90,24 +99,25 @@ msda_fwd_vec_kernel(const float* __restrict__ value, const int64_t* __restrict__
             const float xs[4] = {xy01.x, xy01.z, xy23.x, xy23.z};
             const float ys[4] = {xy01.y, xy01.w, xy23.y, xy23.w};
             const float as[4] = {a4.x, a4.y, a4.z, a4.w};
+            const int rowf = W * pix;               // floats between vertically adjacent pixels (fits int: host check)
             float4 v[P][4];
             float w[P][4];
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                const float x = fmaf(xs[p], (float)W, -0.5f);
-                const float y = fmaf(ys[p], (float)H, -0.5f);
-                const bool inside = (y > -1.f) && (x > -1.f) && (y < (float)H) && (x < (float)W);
+                const float x = fmaf(xs[p], fW, -0.5f);
+                const float y = fmaf(ys[p], fH, -0.5f);
+                const bool inside = (y > -1.f) && (x > -1.f) && (y < fH) && (x < fW);
                 const float xf = floorf(x), yf = floorf(y);
                 const int x0 = (int)xf, y0 = (int)yf;
                 const float lx = x - xf, ly = y - yf, hx = 1.f - lx, hy = 1.f - ly;
                 const bool top = inside && (y0 >= 0), bot = inside && (y0 + 1 <= H - 1);
                 const bool lef = (x0 >= 0), rig = (x0 + 1 <= W - 1);
-                const float* p00 = vl + ((long long)y0 * W + x0) * pix;
+                const float* p00 = vl + (y0 * W + x0) * pix;      // only dereferenced when the predicate holds
                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
                 v[p][0] = (top && lef) ? ldg4(p00) : z;
                 v[p][1] = (top && rig) ? ldg4(p00 + pix) : z;
-                v[p][2] = (bot && lef) ? ldg4(p00 + (long long)W * pix) : z;
-                v[p][3] = (bot && rig) ? ldg4(p00 + (long long)W * pix + pix) : z;
+                v[p][2] = (bot && lef) ? ldg4(p00 + rowf) : z;
+                v[p][3] = (bot && rig) ? ldg4(p00 + rowf + pix) : z;
                 const float a = as[p];
                 w[p][0] = a * (hy * hx);
                 w[p][1] = a * (hy * lx);
@@ -137,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 msda_bwd_vec_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                     const float* __restrict__ attn, const float* __restrict__ grad_out, int S, int M,
-                    int Lq, long long n_units, float* __restrict__ grad_value,
+                    int Lq, long long n_units, long long units_per_block, float* __restrict__ grad_value,
                     float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
     constexpr int D = 4 * LPU;
     constexpr int UPW = 32 / LPU;
@@ -157,12 +167,14 @@ msda_bwd_vec_kernel(const float* __restrict__ value, const int64_t* __restrict__
     const int lane = threadIdx.x & 31;
     const int sub = lane / LPU;
     const int cl = lane % LPU;
-    const long long warp = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-    const long long nwarps = (long long)gridDim.x * (kThreads / 32);
+    const int wib = threadIdx.x >> 5;
     const int pix = M * D;
-    const long long n_iter_units = ((n_units + UPW - 1) / UPW) * UPW;  // keep warps converged for shuffles
+    // contiguous unit range per CTA (L1 / L2-atomic locality, see the forward kernel); ranges are multiples of UPW so
+    // the lanes of a warp stay converged for the shuffles.
+    const long long u_begin = (long long)blockIdx.x * units_per_block;
+    const long long u_end = min(((n_units + UPW - 1) / UPW) * UPW, u_begin + units_per_block);
 
-    for (long long unit = warp * UPW + sub; unit < n_iter_units; unit += nwarps * UPW) {
+    for (long long unit = u_begin + wib * UPW + sub; unit < u_end; unit += (kThreads / 32) * UPW) {
         const bool live = unit < n_units;
         const long long u = live ? unit : 0;
         const int m = (int)(u % M);
@@ -412,12 +424,16 @@ int forward_impl(const T* value, const int64_t* shapes, const int64_t* lsi, cons
         if (fast) {
             const int lpu = D / 4, upw = 32 / lpu;
             const int grid = grid_for((n_units + upw - 1) / upw, 8);
-            if (lpu == 8)
-                msda_fwd_vec_kernel<8><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, S, M, L, Lq, n_units, out);
+            const long long per = (kThreads / 32) * upw;                        // units one CTA pass covers
+            const long long upb = ((n_units + grid - 1) / grid + per - 1) / per * per;
+            if (lpu == 8 && L == 4)
+                msda_fwd_vec_kernel<8, 4><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, S, M, L, Lq, n_units, upb, out);
+            else if (lpu == 8)
+                msda_fwd_vec_kernel<8, 0><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, S, M, L, Lq, n_units, upb, out);
             else if (lpu == 4)
-                msda_fwd_vec_kernel<4><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, S, M, L, Lq, n_units, out);
+                msda_fwd_vec_kernel<4, 0><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, S, M, L, Lq, n_units, upb, out);
             else
-                msda_fwd_vec_kernel<16><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, S, M, L, Lq, n_units, out);
+                msda_fwd_vec_kernel<16, 0><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, S, M, L, Lq, n_units, upb, out);
             return (int)cudaGetLastError();
         }
     }
@@ -454,12 +470,14 @@ int backward_impl(const T* value, const int64_t* shapes, const int64_t* lsi, con
         if (fast) {
             const int lpu = D / 4, upw = 32 / lpu;
             const int grid = grid_for((n_units + upw - 1) / upw, 6);
+            const long long per = (kThreads / 32) * upw;
+            const long long upb = ((n_units + grid - 1) / grid + per - 1) / per * per;
             if (lpu == 8)
-                msda_bwd_vec_kernel<8, 4><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, grad_out, S, M, Lq, n_units, grad_value, grad_loc, grad_attn);
+                msda_bwd_vec_kernel<8, 4><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, grad_out, S, M, Lq, n_units, upb, grad_value, grad_loc, grad_attn);
             else if (lpu == 4)
-                msda_bwd_vec_kernel<4, 4><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, grad_out, S, M, Lq, n_units, grad_value, grad_loc, grad_attn);
+                msda_bwd_vec_kernel<4, 4><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, grad_out, S, M, Lq, n_units, upb, grad_value, grad_loc, grad_attn);
             else
-                msda_bwd_vec_kernel<16, 4><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, grad_out, S, M, Lq, n_units, grad_value, grad_loc, grad_attn);
+                msda_bwd_vec_kernel<16, 4><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, grad_out, S, M, Lq, n_units, upb, grad_value, grad_loc, grad_attn);
             return (int)cudaGetLastError();
         }
     }
