@@ -181,6 +181,11 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         // ================================ MMA issuer ==============================================
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_tf32(BM, BN, A_MN, B_MN);
+            constexpr uint64_t kDescHiA = (A_MN ? make_smem_desc(0, kChunkBytes, 512, 1) : make_smem_desc(0, 16, 1024, 2)) & 0xFFFFFFFF00000000ull;
+            constexpr uint64_t kDescHiB = (B_MN ? make_smem_desc(0, kChunkBytes, 512, 1) : make_smem_desc(0, 16, 1024, 2)) & 0xFFFFFFFF00000000ull;
+            constexpr uint32_t kDescLoA = (uint32_t)((A_MN ? make_smem_desc(0, kChunkBytes, 512, 1) : make_smem_desc(0, 16, 1024, 2)) & 0xFFFF0000ull);
+            constexpr uint32_t kDescLoB = (uint32_t)((B_MN ? make_smem_desc(0, kChunkBytes, 512, 1) : make_smem_desc(0, 16, 1024, 2)) & 0xFFFF0000ull);
+            const uint32_t smem_base_u32 = smem_u32(smem);
             int git = 0, lt = 0;                                  // lt counts tiles that have a main loop
             for (int tix = blockIdx.x; tix < p.total_tiles; tix += gridDim.x) {
                 const Tile t = decode(tix);
@@ -194,22 +199,22 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     const uint32_t ph = (git / STAGES) & 1;
                     mbar_wait(SPLIT ? &split_bar[s] : &full_bar[s], ph);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + s * kStageBytes);
+                    // Descriptors: every field except the 14-bit start address is a per-kernel constant, so a k-step costs
+                    // one add + shift + or per operand (the single issuing thread is otherwise instruction-bound).
+                    // K-major (SWIZZLE_128B): 8 fp32 = 32 B further along the 128-B row; 8-row groups 1024 B apart (SBO).
+                    // MN-major (128B swizzle, 32-B atoms, 4-row period): 8 reduction rows = 1024 B further per k-step;
+                    // 4-row groups 512 B apart (SBO); 32-wide MN chunks 4096 B apart (LBO).
+                    const uint32_t a_addr = smem_base_u32 + s * kStageBytes;
                     const uint32_t b_addr = a_addr + kTileABytes;
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {
-                        // K-major (SWIZZLE_128B): 8 fp32 = 32 B further along the 128-B row; 8-row groups 1024 B apart (SBO).
-                        // MN-major (128B swizzle, 32-B atoms, 4-row period): 8 reduction rows = 1024 B further per k-step;
-                        // 4-row groups 512 B apart (SBO); 32-wide MN chunks 4096 B apart (LBO).
                         const uint32_t ao = A_MN ? k * 1024 : k * 32, bo = B_MN ? k * 1024 : k * 32;
-                        const uint64_t adesc = A_MN ? make_smem_desc(a_addr + ao, kChunkBytes, 512, 1) : make_smem_desc(a_addr + ao, 16, 1024, 2);
-                        const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + bo, kChunkBytes, 512, 1) : make_smem_desc(b_addr + bo, 16, 1024, 2);
+                        const uint64_t adesc = kDescHiA | (uint64_t)(kDescLoA | (((a_addr + ao) >> 4) & 0x3FFFu));
+                        const uint64_t bdesc = kDescHiB | (uint64_t)(kDescLoB | (((b_addr + bo) >> 4) & 0x3FFFu));
                         umma_tf32(tacc, adesc, bdesc, idesc, (it > 0) || (k > 0));
                         if constexpr (SPLIT) {
-                            const uint64_t alo = A_MN ? make_smem_desc(a_addr + kRawBytes + ao, kChunkBytes, 512, 1)
-                                                      : make_smem_desc(a_addr + kRawBytes + ao, 16, 1024, 2);
-                            const uint64_t blo = B_MN ? make_smem_desc(b_addr + kRawBytes + bo, kChunkBytes, 512, 1)
-                                                      : make_smem_desc(b_addr + kRawBytes + bo, 16, 1024, 2);
+                            const uint64_t alo = kDescHiA | (uint64_t)(kDescLoA | (((a_addr + kRawBytes + ao) >> 4) & 0x3FFFu));
+                            const uint64_t blo = kDescHiB | (uint64_t)(kDescLoB | (((b_addr + kRawBytes + bo) >> 4) & 0x3FFFu));
                             umma_tf32(tacc, alo, bdesc, idesc, true);
                             umma_tf32(tacc, adesc, blo, idesc, true);
                         }
@@ -259,7 +264,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         int lt = 0;
         for (int tix = blockIdx.x; tix < p.total_tiles; tix += gridDim.x) {
             const Tile t = decode(tix);
-            size_t roff[8];                    // element offset of (row, column 0) for the 8 rows this lane stores
+            uint32_t roff[8];                  // element offset (fits 32 bit: host check) of (row, column 0), 8 rows per lane
             float rsc[8];
             uint32_t rok = 0;
 #pragma unroll
@@ -271,13 +276,13 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     const int y = t.y0 + ly, x = t.x0 + lx;
                     if ((y < p.Ho) && (x < p.Wo)) rok |= 1u << i;
                     const int oy = y * p.out_sy + p.out_oy, ox = x * p.out_sx + p.out_ox;
-                    roff[i] = (((size_t)t.img * p.out_H + oy) * p.out_W + ox) * (size_t)p.ldo;
+                    roff[i] = (uint32_t)(((t.img * p.out_H + oy) * p.out_W + ox) * p.ldo);
                 } else {
                     if ((t.m0 + row) < p.Mo_rows) {
                         rok |= 1u << i;
                         if (p.rowscale) rsc[i] = p.rowscale[t.m0 + row];
                     }
-                    roff[i] = (size_t)(t.m0 + row) * p.ldo;
+                    roff[i] = (uint32_t)((t.m0 + row) * p.ldo);
                 }
             }
             const int slot = lt & 1;
@@ -286,21 +291,28 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 tc_fence_after();
             }
             const uint32_t taddr_row = tmem_base + slot * BN + ((uint32_t)(q * 32) << 16);
+            const float* prow = patch + r4 * kPatchLd + c4 * 4;          // this lane's read window into the transposed patch
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 if (t.n0 + c0 >= p.No) break;  // uniform across the CTA
-                // Issue every global read of this chunk (residual, ReLU mask, bias) BEFORE waiting on TMEM, through the
-                // read-only path, so their latency overlaps instead of serialising 32 dependent loads per thread.
                 const int n = t.n0 + c0 + c4 * 4;
-                const bool vec = (n + 3 < p.No);
+                const bool full = (t.n0 + c0 + 32 <= p.No);             // uniform: every lane's float4 is in range
+                // Issue the global reads of this chunk (residual / ReLU mask / bias, read-only path) BEFORE waiting on
+                // TMEM so their latency overlaps; the two flags are uniform, the bodies are specialised below.
                 float4 res[8], msk[8];
                 float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias && vec) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                if (full) {
+                    if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                    if (p.residual) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const bool ok = ((rok >> i) & 1u) && vec;
-                    res[i] = (p.residual && ok) ? __ldg(reinterpret_cast<const float4*>(p.residual + roff[i] + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    msk[i] = (p.relu_mask && ok) ? __ldg(reinterpret_cast<const float4*>(p.relu_mask + roff[i] + n)) : make_float4(1.f, 1.f, 1.f, 1.f);
+                        for (int i = 0; i < 8; ++i)
+                            if ((rok >> i) & 1u) res[i] = __ldg(reinterpret_cast<const float4*>(p.residual + roff[i] + n));
+                    }
+                    if (p.relu_mask) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if ((rok >> i) & 1u) msk[i] = __ldg(reinterpret_cast<const float4*>(p.relu_mask + roff[i] + n));
+                    }
                 }
                 uint32_t r[32];
                 if (t.iters > 0) {
@@ -314,36 +326,40 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<uint4*>(patch + lane * kPatchLd + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                 __syncwarp();
+                if (full) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (!((rok >> i) & 1u) || n >= p.No) continue;
-                    const float4 a = *reinterpret_cast<const float4*>(patch + (i * 4 + r4) * kPatchLd + c4 * 4);
-                    float v[4] = {a.x * rsc[i], a.y * rsc[i], a.z * rsc[i], a.w * rsc[i]};
-                    const size_t o = roff[i] + n;
-                    if (vec) {
-                        v[0] += bias4.x + res[i].x; v[1] += bias4.y + res[i].y; v[2] += bias4.z + res[i].z; v[3] += bias4.w + res[i].w;
-                        if (p.relu) {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+                    for (int i = 0; i < 8; ++i) {
+                        if (!((rok >> i) & 1u)) continue;
+                        const float4 a = *reinterpret_cast<const float4*>(prow + i * 4 * kPatchLd);
+                        float4 v = make_float4(fmaf(a.x, rsc[i], bias4.x), fmaf(a.y, rsc[i], bias4.y), fmaf(a.z, rsc[i], bias4.z),
+                                               fmaf(a.w, rsc[i], bias4.w));
+                        if (p.residual) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+                        if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        if (p.relu_mask) {
+                            v.x = msk[i].x > 0.f ? v.x : 0.f; v.y = msk[i].y > 0.f ? v.y : 0.f;
+                            v.z = msk[i].z > 0.f ? v.z : 0.f; v.w = msk[i].w > 0.f ? v.w : 0.f;
                         }
-                        v[0] = msk[i].x > 0.f ? v[0] : 0.f; v[1] = msk[i].y > 0.f ? v[1] : 0.f;
-                        v[2] = msk[i].z > 0.f ? v[2] : 0.f; v[3] = msk[i].w > 0.f ? v[3] : 0.f;
-                        if (p.round_out) {
+                        if (p.round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+                        float* dst = p.out + roff[i] + n;
+                        if (p.atomic_out) red_add_v4_f32(dst, v.x, v.y, v.z, v.w);
+                        else *reinterpret_cast<float4*>(dst) = v;
+                    }
+                } else {
+                    // ragged right edge (No not a multiple of 32): scalar path, rare (head outputs, padded N)
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) v[e] = round_tf32(v[e]);
-                        }
-                        if (p.atomic_out) red_add_v4_f32(p.out + o, v[0], v[1], v[2], v[3]);
-                        else *reinterpret_cast<float4*>(p.out + o) = make_float4(v[0], v[1], v[2], v[3]);
-                    } else {
+                    for (int i = 0; i < 8; ++i) {
+                        if (!((rok >> i) & 1u)) continue;
+#pragma unroll 1
                         for (int e = 0; e < 4 && n + e < p.No; ++e) {
-                            float x = v[e];
+                            const size_t o = (size_t)roff[i] + n + e;
+                            float x = prow[i * 4 * kPatchLd + e] * rsc[i];
                             if (p.bias) x += p.bias[n + e];
-                            if (p.residual) x += p.residual[o + e];
+                            if (p.residual) x += p.residual[o];
                             if (p.relu) x = fmaxf(x, 0.f);
-                            if (p.relu_mask) x = p.relu_mask[o + e] > 0.f ? x : 0.f;
+                            if (p.relu_mask) x = p.relu_mask[o] > 0.f ? x : 0.f;
                             if (p.round_out) x = round_tf32(x);
-                            if (p.atomic_out) atomicAdd(p.out + o + e, x);
-                            else p.out[o + e] = x;
+                            if (p.atomic_out) atomicAdd(p.out + o, x);
+                            else p.out[o] = x;
                         }
                     }
                 }
