@@ -47,7 +47,7 @@ struct TcParams {
     // ---- wgrad: reduction over pixel tiles of 32 (rth x rtw), split across blockIdx.z ----------
     int rtiles_x, rtiles_y, rtw, rth, n_img, red_per_split;
     int total_tiles, n_tiles_n, n_tiles_m;   // persistent tile walk: tile = (z * n_tiles_m + m) * n_tiles_n + n
-    int w_dy, w_dx, w_sy, w_sx;      // X-box origin = (y0*w_sy + w_dy, x0*w_sx + w_dx)  (per launch = per tap)
+    int w_sy, w_sx, wg_taps, wg_kw, wg_pad;   // X-box origin = (y0*w_sy + ky - pad, x0*w_sx + kx - pad); all taps in ONE launch
     // ---- epilogue -----------------------------------------------------------------------------
     int Mo_rows;                     // wgrad: number of valid output rows (Cout)
     int No, ldo;
@@ -91,12 +91,12 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int lane = threadIdx.x & 31;
 
     // ---- tile decode (identical in every role) -----------------------------------------------------
-    struct Tile { int n0, img, y0, x0, m0, red_begin, iters; };
+    struct Tile { int n0, img, y0, x0, m0, red_begin, iters, tap; };
     auto decode = [&](int tix) {
         Tile t;
         t.n0 = (tix % p.n_tiles_n) * BN;
         int r = tix / p.n_tiles_n;
-        t.img = t.y0 = t.x0 = t.m0 = t.red_begin = 0;
+        t.img = t.y0 = t.x0 = t.m0 = t.red_begin = t.tap = 0;
         if constexpr (MODE == 0) {
             const int per_img = p.tiles_x * p.tiles_y;
             t.img = r / per_img;
@@ -106,7 +106,9 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             t.iters = p.ntaps * p.cblocks;
         } else {
             t.m0 = (r % p.n_tiles_m) * BM;
-            const int z = r / p.n_tiles_m;
+            r /= p.n_tiles_m;
+            t.tap = r % p.wg_taps;
+            const int z = r / p.wg_taps;
             const int total_red = p.n_img * p.rtiles_x * p.rtiles_y;
             t.red_begin = z * p.red_per_split;
             t.iters = max(0, min(total_red, t.red_begin + p.red_per_split) - t.red_begin);
@@ -171,8 +173,8 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                             tma_load_4d(a_dst + j * kChunkBytes, &mapA, &full_bar[s], t.m0 + j * 32, rx, ry, ri);
 #pragma unroll
                         for (int j = 0; j < BN / 32; ++j)
-                            tma_load_4d(b_dst + j * kChunkBytes, &mapB, &full_bar[s], t.n0 + j * 32, rx * p.w_sx + p.w_dx,
-                                        ry * p.w_sy + p.w_dy, ri);
+                            tma_load_4d(b_dst + j * kChunkBytes, &mapB, &full_bar[s], t.n0 + j * 32,
+                                        rx * p.w_sx + (t.tap % p.wg_kw) - p.wg_pad, ry * p.w_sy + (t.tap / p.wg_kw) - p.wg_pad, ri);
                     }
                 }
             }
@@ -282,7 +284,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         rok |= 1u << i;
                         if (p.rowscale) rsc[i] = p.rowscale[t.m0 + row];
                     }
-                    roff[i] = (uint32_t)((t.m0 + row) * p.ldo);
+                    roff[i] = (uint32_t)((t.tap * p.Mo_rows + t.m0 + row) * p.ldo);
                 }
             }
             const int slot = lt & 1;
@@ -520,6 +522,7 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
             const int t = ky * kw + kx;
             p.tap_dy[t] = ky - pad; p.tap_dx[t] = kx - pad; p.tap_w[t] = t;
         }
+    p.wg_taps = 1; p.wg_kw = 1;
     p.No = Cout; p.ldo = Cout; p.relu = flags & 1; p.round_out = (g_precision == 0) ? ((flags >> 1) & 1) : 0; p.atomic_out = 0;
     p.bias = bias; p.residual = residual; p.relu_mask = nullptr; p.rowscale = nullptr; p.out = y;
 
@@ -588,6 +591,7 @@ int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* re
                 }
             }
             p.ntaps = nt;
+            p.wg_taps = 1; p.wg_kw = 1;
             p.No = Cin; p.ldo = Cin; p.relu = 0; p.atomic_out = 0; p.round_out = (g_precision == 0) ? ((flags >> 1) & 1) : 0;
             p.bias = nullptr; p.residual = residual; p.relu_mask = relu_mask; p.rowscale = nullptr; p.out = dx;
             CUtensorMap ma, mb;
@@ -639,14 +643,19 @@ int mdb_conv2d_wgrad_f32(const float* dy, const float* x, const float* rowscale,
     const int total_red = B * p.rtiles_x * p.rtiles_y;
     const int bn = (g_precision == 0 && Cin >= 256) ? 256 : 128;
     const int tiles = ((Cout + BM - 1) / BM) * ((Cin + bn - 1) / bn) * taps;
-    int splits = (296 + tiles - 1) / tiles;            // aim at ~2 waves of 148 SMs
-    if (splits > total_red) splits = total_red;
+    // split-K over pixel tiles: enough CTAs to fill the machine (~2 waves), but at least ~24 reduction steps per CTA so
+    // the 128 x BN atomic epilogue stays a small fraction of the work.
+    int splits = (2 * num_sms_tc() + tiles - 1) / tiles;
+    const int max_splits = total_red / 24 > 0 ? total_red / 24 : 1;
+    if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     p.red_per_split = (total_red + splits - 1) / splits;
     splits = (total_red + p.red_per_split - 1) / p.red_per_split;
     p.w_sy = p.w_sx = stride;
+    p.wg_taps = taps; p.wg_kw = kw; p.wg_pad = pad;
     p.Mo_rows = Cout; p.No = Cin; p.ldo = Cin; p.relu = 0; p.atomic_out = 1;
     p.bias = nullptr; p.residual = nullptr; p.relu_mask = nullptr; p.rowscale = rowscale;
+    p.out = dw_packed;
 
     CUtensorMap ma, mb;
     {   // A (MN-major): dy as (Cout, Wo, Ho, B); box = 32 channels x (rtw x rth) reduction pixels
@@ -664,16 +673,11 @@ int mdb_conv2d_wgrad_f32(const float* dy, const float* x, const float* rowscale,
         rc = make_map(&mb, x, 4, dims, str, box, es, true);
         if (rc) return rc;
     }
-    for (int t = 0; t < taps; ++t) {
-        p.w_dy = t / kw - pad;
-        p.w_dx = t % kw - pad;
-        p.out = dw_packed + (size_t)t * Cout * Cin;
-        dim3 grid((Cin + bn - 1) / bn, (Cout + BM - 1) / BM, splits);
-        rc = (g_precision == 1) ? launch_tc<128, 3, 1, true, true>(ma, mb, p, grid, stream)
-             : (bn == 256)      ? launch_tc<256, 4, 1, true, false>(ma, mb, p, grid, stream)
-                                : launch_tc<128, 5, 1, true, false>(ma, mb, p, grid, stream);
-        if (rc) return rc;
-    }
+    dim3 grid((Cin + bn - 1) / bn, (Cout + BM - 1) / BM, taps * splits);
+    rc = (g_precision == 1) ? launch_tc<128, 3, 1, true, true>(ma, mb, p, grid, stream)
+         : (bn == 256)      ? launch_tc<256, 4, 1, true, false>(ma, mb, p, grid, stream)
+                            : launch_tc<128, 5, 1, true, false>(ma, mb, p, grid, stream);
+    if (rc) return rc;
     return 0;
 }
 
