@@ -316,6 +316,7 @@ def run_reference(args, rank, ws):
         cfg = {"workload": f"msda core fwd+bwd, Lq={args.lq}, reference CPU path (grid_sample) port"}
     else:
         from oracle import monodetr_torch as om
+        args.cpu_batch = 1
         val, dt, sample, threads, cfg = om.bench_reference_model(args)
     return {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/sec", "n_gpus": ws,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
