@@ -60,6 +60,17 @@ int mdb_msda_backward_f64(const double* value, const int64_t* spatial_shapes, co
                           int B, int S, int M, int D, int L, int Lq, int P,
                           double* grad_value, double* grad_loc, double* grad_attn, void* stream);
 
+/* Fused MSDeformAttn pre-processing (ops/modules/ms_deform_attn.py:145-155): sampling_locations and
+ * softmax(attention logits) from the raw projections in one pass, and its backward.
+ * off (B,Lq,M,L,P,2), logits (B,Lq,M,L*P), ref (B,Lq,L,ref_dim) contiguous, ref_dim in {2,6}; L*P <= 16.
+ * backward: doff / dlogits from dloc / dattn (+ saved attn); the gradient wrt ref (only decoder layer 0 needs it)
+ * is a plain reduction of dloc done by the caller. */
+int mdb_msda_prep_forward_f32(const float* off, const float* logits, const float* ref, const int64_t* spatial_shapes,
+                              int B, int Lq, int M, int L, int P, int ref_dim, float* loc, float* attn, void* stream);
+int mdb_msda_prep_backward_f32(const float* dloc, const float* dattn, const float* attn, const float* ref,
+                               const int64_t* spatial_shapes, int B, int Lq, int M, int L, int P, int ref_dim,
+                               float* doff, float* dlogits, void* stream);
+
 /* ---- Tensor-core convolution / linear family (tcgen05 + TMEM + TMA, fp32 storage, TF32 math) ----
  * Replaces the cuDNN / cuBLAS calls behind nn.Conv2d / nn.Linear on the reference path
  * (backbone.py:100-102; monodetr.py:83-91; depth_predictor/depth_predictor.py:29-47;

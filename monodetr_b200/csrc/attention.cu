@@ -13,8 +13,9 @@
 // Mapping: register-resident warp-level tensor-core tiles (mma.sync m16n8k8 TF32, fp32 accumulate).  A CTA of
 // 4 warps owns 64 rows (queries, or keys in the dK/dV kernel); each warp owns 16 rows and streams 64-row tiles
 // of the other operand through padded shared memory (row stride 36 floats: conflict-free fragment loads).
-// Scores use error-compensated 3xTF32 (hi/lo split in registers) so exp() sees fp32-accurate logits; P.V uses
-// the same in the forward pass.  The P (C-fragment) -> A-fragment hand-off needs no shuffles: the k index of the
+// Scores (forward AND the recomputation in backward) use error-compensated 3xTF32 (hi/lo split in registers) so
+// exp() sees fp32-accurate logits; P.V uses the same in the forward pass; the four gradient contractions of the
+// backward pass are single-pass TF32 with round-to-nearest operands (measured 8e-4 of max|grad|).  The P (C-fragment) -> A-fragment hand-off needs no shuffles: the k index of the
 // second GEMM is permuted (col t <-> key 2t, col t+4 <-> key 2t+1) and V/K/dO/Q rows are fetched in that order.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -288,7 +289,7 @@ attn_bwd_dq_kernel(const AttnParams p) {
         __syncthreads();
         float s[8][4], dp[8][4];
         gemm_nt<3>(s, qa, sK, lane);
-        gemm_nt<3>(dp, ga, sV, lane);
+        gemm_nt<1>(dp, ga, sV, lane);          // gradients: single-pass TF32 with round-to-nearest operands
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -306,7 +307,7 @@ attn_bwd_dq_kernel(const AttnParams p) {
                 s[nt][2 + e] = p1 * (d1 - dl1);
             }
         }
-        gemm_nn<3>(acc, s, sK, lane);
+        gemm_nn<1>(acc, s, sK, lane);
     }
     float* ob = p.dq + (size_t)b * p.Lq * p.lddq + h * HD;
 #pragma unroll
@@ -358,7 +359,7 @@ attn_bwd_dkv_kernel(const AttnParams p) {
         __syncthreads();
         float s[8][4], dp[8][4];
         gemm_nt<3>(s, ka, sQ, lane);          // S^T[key][query] (already scaled through K)
-        gemm_nt<3>(dp, va, sG, lane);         // dP^T[key][query] = V . dO^T
+        gemm_nt<1>(dp, va, sG, lane);         // dP^T[key][query] = V . dO^T
         float pd[8][4];                        // dropped probabilities for dV
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
@@ -380,8 +381,8 @@ attn_bwd_dkv_kernel(const AttnParams p) {
                 s[nt][2 + e] = p1 * (d1 - dl);
             }
         }
-        gemm_nn<3>(dv, pd, sG, lane);          // dV += P^T_dropped . dO
-        gemm_nn<3>(dk, s, sQ, lane);           // dK += dS^T . Q
+        gemm_nn<1>(dv, pd, sG, lane);          // dV += P^T_dropped . dO
+        gemm_nn<1>(dk, s, sQ, lane);           // dK += dS^T . Q
     }
     float* dkb = p.dk + (size_t)b * p.Lk * p.lddk + h * HD;
     float* dvb = p.dv + (size_t)b * p.Lk * p.lddv + h * HD;

@@ -514,3 +514,134 @@ int mdb_msda_backward_f64(const double* value, const int64_t* spatial_shapes, co
 }
 
 }  // extern "C"
+
+// =================================================================================================
+// Fused pre-processing of the MSDeformAttn module (ops/modules/ms_deform_attn.py:145-155): from the raw
+// projections  off = sampling_offsets(query) [.., M, L, P, 2]  and  logits = attention_weights(query) [.., M, L*P]
+// produce  sampling_locations  and  softmax(logits)  in one pass (the reference runs ~6 elementwise kernels
+// over these 83 MB tensors), and the matching backward.
+//   ref_dim == 2:  loc = ref[b,q,l,:] + off / (W_l, H_l)
+//   ref_dim == 6:  loc = ref_xy + off / P * (ref[2]+ref[3], ref[4]+ref[5]) * 0.5      (l+r, t+b)
+// One thread per (b, q, m); L*P <= 16.
+// =================================================================================================
+namespace {
+
+constexpr int kPrepMaxLP = 16;
+
+__global__ void __launch_bounds__(256)
+msda_prep_fwd_kernel(const float* __restrict__ off, const float* __restrict__ logits, const float* __restrict__ ref,
+                     const int64_t* __restrict__ shapes, int M, int L, int P, int ref_dim, long long n_units,
+                     float* __restrict__ loc, float* __restrict__ attn) {
+    const int LP = L * P;
+    for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < n_units; u += (long long)gridDim.x * blockDim.x) {
+        const long long bq = u / M;
+        const float* o = off + u * LP * 2;
+        const float* lg = logits + u * LP;
+        float* lo = loc + u * LP * 2;
+        float* at = attn + u * LP;
+        float v[kPrepMaxLP];
+        float mx = -INFINITY;
+        for (int i = 0; i < LP; i += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(lg + i);
+            v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+            mx = fmaxf(mx, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
+        }
+        float sum = 0.f;
+        for (int i = 0; i < LP; ++i) { v[i] = expf(v[i] - mx); sum += v[i]; }
+        const float inv = 1.f / sum;
+        for (int i = 0; i < LP; i += 4)
+            *reinterpret_cast<float4*>(at + i) = make_float4(v[i] * inv, v[i + 1] * inv, v[i + 2] * inv, v[i + 3] * inv);
+        for (int l = 0; l < L; ++l) {
+            const float* r = ref + (bq * L + l) * ref_dim;
+            float sx, sy;
+            if (ref_dim == 2) {
+                sx = 1.f / (float)shapes[2 * l + 1];
+                sy = 1.f / (float)shapes[2 * l];
+            } else {
+                sx = (r[2] + r[3]) * 0.5f / (float)P;
+                sy = (r[4] + r[5]) * 0.5f / (float)P;
+            }
+            const float rx = r[0], ry = r[1];
+            for (int p = 0; p < P; p += 2) {
+                const float4 t = *reinterpret_cast<const float4*>(o + (l * P + p) * 2);
+                float4 w;
+                if (ref_dim == 2) { w.x = rx + t.x / (float)shapes[2 * l + 1]; w.y = ry + t.y / (float)shapes[2 * l];
+                                    w.z = rx + t.z / (float)shapes[2 * l + 1]; w.w = ry + t.w / (float)shapes[2 * l]; }
+                else { w.x = fmaf(t.x, sx, rx); w.y = fmaf(t.y, sy, ry); w.z = fmaf(t.z, sx, rx); w.w = fmaf(t.w, sy, ry); }
+                *reinterpret_cast<float4*>(lo + (l * P + p) * 2) = w;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+msda_prep_bwd_kernel(const float* __restrict__ dloc, const float* __restrict__ dattn, const float* __restrict__ attn,
+                     const float* __restrict__ ref, const int64_t* __restrict__ shapes, int M, int L, int P, int ref_dim,
+                     long long n_units, float* __restrict__ doff, float* __restrict__ dlogits) {
+    const int LP = L * P;
+    for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < n_units; u += (long long)gridDim.x * blockDim.x) {
+        const long long bq = u / M;
+        float a[kPrepMaxLP], g[kPrepMaxLP];
+        float dot = 0.f;
+        for (int i = 0; i < LP; i += 4) {
+            const float4 x = *reinterpret_cast<const float4*>(attn + u * LP + i);
+            const float4 y = *reinterpret_cast<const float4*>(dattn + u * LP + i);
+            a[i] = x.x; a[i + 1] = x.y; a[i + 2] = x.z; a[i + 3] = x.w;
+            g[i] = y.x; g[i + 1] = y.y; g[i + 2] = y.z; g[i + 3] = y.w;
+            dot += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+        }
+        for (int i = 0; i < LP; i += 4)
+            *reinterpret_cast<float4*>(dlogits + u * LP + i) = make_float4(a[i] * (g[i] - dot), a[i + 1] * (g[i + 1] - dot),
+                                                                          a[i + 2] * (g[i + 2] - dot), a[i + 3] * (g[i + 3] - dot));
+        for (int l = 0; l < L; ++l) {
+            float sx, sy;
+            if (ref_dim == 2) {
+                sx = 1.f / (float)shapes[2 * l + 1];
+                sy = 1.f / (float)shapes[2 * l];
+            } else {
+                const float* r = ref + (bq * L + l) * ref_dim;
+                sx = (r[2] + r[3]) * 0.5f / (float)P;
+                sy = (r[4] + r[5]) * 0.5f / (float)P;
+            }
+            for (int p = 0; p < P; p += 2) {
+                const float4 t = *reinterpret_cast<const float4*>(dloc + (u * LP + l * P + p) * 2);
+                float4 w;
+                if (ref_dim == 2) { w.x = t.x / (float)shapes[2 * l + 1]; w.y = t.y / (float)shapes[2 * l];
+                                    w.z = t.z / (float)shapes[2 * l + 1]; w.w = t.w / (float)shapes[2 * l]; }
+                else { w.x = t.x * sx; w.y = t.y * sy; w.z = t.z * sx; w.w = t.w * sy; }
+                *reinterpret_cast<float4*>(doff + (u * LP + l * P + p) * 2) = w;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int mdb_msda_prep_forward_f32(const float* off, const float* logits, const float* ref, const int64_t* spatial_shapes,
+                              int B, int Lq, int M, int L, int P, int ref_dim, float* loc, float* attn, void* stream) {
+    if (!off || !logits || !ref || !spatial_shapes || !loc || !attn) return MDB_EINVAL;
+    if (L * P > kPrepMaxLP || (L * P) % 4 || P % 2 || (ref_dim != 2 && ref_dim != 6)) return MDB_EUNSUPPORTED;
+    const long long n = (long long)B * Lq * M;
+    if (n == 0) return 0;
+    long long g = (n + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    msda_prep_fwd_kernel<<<(int)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(off, logits, ref, spatial_shapes, M, L, P, ref_dim, n, loc, attn);
+    return (int)cudaGetLastError();
+}
+
+int mdb_msda_prep_backward_f32(const float* dloc, const float* dattn, const float* attn, const float* ref,
+                               const int64_t* spatial_shapes, int B, int Lq, int M, int L, int P, int ref_dim,
+                               float* doff, float* dlogits, void* stream) {
+    if (!dloc || !dattn || !attn || !ref || !spatial_shapes || !doff || !dlogits) return MDB_EINVAL;
+    if (L * P > kPrepMaxLP || (L * P) % 4 || P % 2 || (ref_dim != 2 && ref_dim != 6)) return MDB_EUNSUPPORTED;
+    const long long n = (long long)B * Lq * M;
+    if (n == 0) return 0;
+    long long g = (n + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    msda_prep_bwd_kernel<<<(int)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(dloc, dattn, attn, ref, spatial_shapes, M, L, P, ref_dim, n, doff, dlogits);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -232,3 +232,46 @@ def attention(q, k, v, key_padding_mask=None, drop_p=0.0, training=False, site=0
 
 def msda(value, spatial_shapes, level_start_index, sampling_locations, attention_weights):
     return MSDeformAttnFunction.apply(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, 64)
+
+
+class _MsdaPrep(Function):
+    """(off, logits, ref) -> (sampling_locations, softmax attention weights); see csrc/msda.cu "Fused pre-processing"."""
+
+    @staticmethod
+    def forward(ctx, off, logits, ref, shapes, M, L, P):
+        B, Lq = off.shape[0], off.shape[1]
+        off = off.contiguous()
+        logits = logits.contiguous()
+        refc = ref.contiguous()
+        rd = refc.shape[-1]
+        loc = torch.empty((B, Lq, M, L, P, 2), dtype=torch.float32, device=off.device)
+        attn = torch.empty((B, Lq, M, L, P), dtype=torch.float32, device=off.device)
+        _lib.check(_lib.lib().mdb_msda_prep_forward_f32(_p(off), _p(logits), _p(refc), _p(shapes), B, Lq, M, L, P, rd, _p(loc),
+                                                        _p(attn), _s()), "msda_prep_forward")
+        _lib.count(1)
+        ctx.save_for_backward(attn, refc, shapes)
+        ctx.meta = (B, Lq, M, L, P, rd, off.shape, logits.shape)
+        return loc, attn
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dloc, dattn):
+        attn, refc, shapes = ctx.saved_tensors
+        B, Lq, M, L, P, rd, oshape, lshape = ctx.meta
+        dloc = dloc.contiguous()
+        dattn = dattn.contiguous()
+        doff = torch.empty(oshape, dtype=torch.float32, device=dloc.device)
+        dlogits = torch.empty(lshape, dtype=torch.float32, device=dloc.device)
+        _lib.check(_lib.lib().mdb_msda_prep_backward_f32(_p(dloc), _p(dattn), _p(attn), _p(refc), _p(shapes), B, Lq, M, L, P, rd,
+                                                         _p(doff), _p(dlogits), _s()), "msda_prep_backward")
+        _lib.count(1)
+        dref = None
+        if ctx.needs_input_grad[2]:
+            if rd != 2:
+                raise RuntimeError("gradient wrt 6-d reference boxes is not needed on this path (they are detached)")
+            dref = dloc.sum(dim=(2, 4))                                   # (B, Lq, L, 2)
+        return doff, dlogits, dref, None, None, None, None
+
+
+def msda_prep(off, logits, ref, spatial_shapes, M, L, P):
+    return _MsdaPrep.apply(off, logits, ref, spatial_shapes, M, L, P)

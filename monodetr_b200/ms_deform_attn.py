@@ -50,20 +50,13 @@ class MSDeformAttn(nn.Module):
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
         value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
-        sampling_offsets = Fn.linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias) \
-            .view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
-        attention_weights = Fn.linear(query, self.attention_weights.weight, self.attention_weights.bias) \
-            .view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
-        attention_weights = F.softmax(attention_weights, -1).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
-        if reference_points.shape[-1] == 2:
-            offset_normalizer = torch.stack([input_spatial_shapes[..., 1], input_spatial_shapes[..., 0]], -1).to(query.dtype)
-            sampling_locations = reference_points[:, :, None, :, None, :] \
-                + sampling_offsets / offset_normalizer[None, None, None, :, None, :]
-        elif reference_points.shape[-1] == 6:
-            sampling_locations = reference_points[:, :, None, :, None, :2] + sampling_offsets / self.n_points * (
-                reference_points[:, :, None, :, None, 2::2] + reference_points[:, :, None, :, None, 3::2]) * 0.5
-        else:
+        sampling_offsets = Fn.linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias)
+        attention_logits = Fn.linear(query, self.attention_weights.weight, self.attention_weights.bias)
+        if reference_points.shape[-1] not in (2, 6):
             raise ValueError(f"Last dim of reference_points must be 2 or 6, but get {reference_points.shape[-1]} instead.")
-        output = Fn.msda(value, input_spatial_shapes, input_level_start_index, sampling_locations.contiguous(),
-                         attention_weights.contiguous())
+        # :145-155 fused: softmax over the 16 (level, point) logits and loc = ref + off / (W_l, H_l)   [2-d refs]
+        #                                                     or ref_xy + off / P * (l+r, t+b) / 2    [6-d refs]
+        sampling_locations, attention_weights = Fn.msda_prep(sampling_offsets, attention_logits, reference_points,
+                                                            input_spatial_shapes, self.n_heads, self.n_levels, self.n_points)
+        output = Fn.msda(value, input_spatial_shapes, input_level_start_index, sampling_locations, attention_weights)
         return Fn.linear(output, self.output_proj.weight, self.output_proj.bias)
