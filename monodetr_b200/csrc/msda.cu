@@ -20,6 +20,7 @@
 // Generic path (any D/L/P, fp32 and fp64): one warp per unit, lanes stride over channels.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/monodetr_b200.h"
 
@@ -136,6 +137,114 @@ msda_fwd_vec_kernel(const float* __restrict__ value, const int64_t* __restrict__
             }
         }
         *reinterpret_cast<float4*>(out + (size_t)unit * D + cl * 4) = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward, D = 32 (8 lanes per unit), L = 4, P = 4: "distributed point set-up".  The 16 sample points of a unit
+// need ~45 integer/float instructions each (coordinates, floor, clamping, 4 corner weights, offsets); doing that in
+// all 8 lanes of the unit made the kernel issue-bound.  Here lane c of the unit prepares points c and c+8 only and
+// the 7 resulting words per point are broadcast inside the octet with width-8 shuffles; corners outside the image are
+// redirected to a clamped (valid) address with weight 0, so no load is predicated and all 16 LDG.128 of a level
+// stay in flight.
+// ------------------------------------------------------------------------------------------------
+struct PointSetup {
+    int o00, dxo, dyo;      // float offset of corner (y0,x0) inside the (b, m) slice; +dxo -> x0+1, +dyo -> y0+1
+    float w[4];             // attention * bilinear weight per corner, 0 for corners outside the image
+};
+
+__device__ __forceinline__ PointSetup setup_point(float lx_, float ly_, float a, int H, int W, int start, int pix) {
+    PointSetup s;
+    const float fW = (float)W, fH = (float)H;
+    const float x = fmaf(lx_, fW, -0.5f), y = fmaf(ly_, fH, -0.5f);
+    const bool inside = (y > -1.f) && (x > -1.f) && (y < fH) && (x < fW);
+    const float xf = floorf(x), yf = floorf(y);
+    const int x0 = inside ? (int)xf : 0, y0 = inside ? (int)yf : 0;
+    const float lx = x - xf, ly = y - yf, hx = 1.f - lx, hy = 1.f - ly;
+    const bool top = inside && (y0 >= 0), bot = inside && (y0 + 1 <= H - 1);
+    const bool lef = (x0 >= 0), rig = (x0 + 1 <= W - 1);
+    const int xc0 = max(x0, 0), yc0 = max(y0, 0);
+    const int xc1 = min(x0 + 1, W - 1), yc1 = min(y0 + 1, H - 1);
+    s.o00 = (start + yc0 * W + xc0) * pix;
+    s.dxo = (max(xc1, xc0) - xc0) * pix;
+    s.dyo = (max(yc1, yc0) - yc0) * W * pix;
+    s.w[0] = (top && lef) ? a * (hy * hx) : 0.f;
+    s.w[1] = (top && rig) ? a * (hy * lx) : 0.f;
+    s.w[2] = (bot && lef) ? a * (ly * hx) : 0.f;
+    s.w[3] = (bot && rig) ? a * (ly * lx) : 0.f;
+    return s;
+}
+
+__global__ void __launch_bounds__(kThreads)
+msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                    const int64_t* __restrict__ lsi, const float* __restrict__ loc,
+                    const float* __restrict__ attn, int S, int M, int Lq, long long n_units,
+                    long long units_per_block, float* __restrict__ out) {
+    constexpr int L = 4, P = 4, D = 32, UPW = 4;
+    __shared__ LevelInfo lv;
+    if (threadIdx.x < L) {
+        lv.H[threadIdx.x] = (int)shapes[2 * threadIdx.x];
+        lv.W[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
+        lv.start[threadIdx.x] = (int)lsi[threadIdx.x];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int sub = lane >> 3, cl = lane & 7;
+    const int wib = threadIdx.x >> 5;
+    const int pix = M * D;
+    const long long u_begin = (long long)blockIdx.x * units_per_block;
+    const long long u_end = min(((n_units + UPW - 1) / UPW) * UPW, u_begin + units_per_block);   // multiple of 4: warps stay converged
+    // this lane prepares points (l = cl/4, p = cl%4) and (l = 2 + cl/4, p = cl%4)
+    const int lA = cl >> 2, lB = 2 + (cl >> 2);
+    const int HA = lv.H[lA], WA = lv.W[lA], sA = lv.start[lA];
+    const int HB = lv.H[lB], WB = lv.W[lB], sB = lv.start[lB];
+
+    for (long long unit = u_begin + wib * UPW + sub; unit < u_end; unit += (kThreads / 32) * UPW) {
+        const bool live = unit < n_units;
+        const long long u = live ? unit : 0;
+        const int m = (int)(u % M);
+        const int b = (int)(u / ((long long)Lq * M));
+        const float* vb = value + ((size_t)b * S * M + m) * D + cl * 4;
+        const float2 xyA = __ldg(reinterpret_cast<const float2*>(loc + (size_t)u * (L * P * 2)) + cl);
+        const float2 xyB = __ldg(reinterpret_cast<const float2*>(loc + (size_t)u * (L * P * 2)) + 8 + cl);
+        const float aA = __ldg(attn + (size_t)u * (L * P) + cl), aB = __ldg(attn + (size_t)u * (L * P) + 8 + cl);
+        const PointSetup A = setup_point(xyA.x, xyA.y, aA, HA, WA, sA, pix);
+        const PointSetup Bp = setup_point(xyB.x, xyB.y, aB, HB, WB, sB, pix);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const PointSetup& Sx = half ? Bp : A;
+#pragma unroll
+            for (int jg = 0; jg < 2; ++jg) {             // 4 points = 16 line loads in flight at a time
+                float4 v[4][4];
+                float w[4][4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = jg * 4 + jj;
+                    const int o00 = __shfl_sync(0xffffffffu, Sx.o00, j, 8);
+                    const int dxo = __shfl_sync(0xffffffffu, Sx.dxo, j, 8);
+                    const int dyo = __shfl_sync(0xffffffffu, Sx.dyo, j, 8);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) w[jj][k] = __shfl_sync(0xffffffffu, Sx.w[k], j, 8);
+                    const float* p00 = vb + o00;
+                    v[jj][0] = ldg4(p00);
+                    v[jj][1] = ldg4(p00 + dxo);
+                    v[jj][2] = ldg4(p00 + dyo);
+                    v[jj][3] = ldg4(p00 + dyo + dxo);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        acc.x = fmaf(w[jj][k], v[jj][k].x, acc.x);
+                        acc.y = fmaf(w[jj][k], v[jj][k].y, acc.y);
+                        acc.z = fmaf(w[jj][k], v[jj][k].z, acc.z);
+                        acc.w = fmaf(w[jj][k], v[jj][k].w, acc.w);
+                    }
+                }
+            }
+        }
+        if (live) *reinterpret_cast<float4*>(out + (size_t)unit * D + cl * 4) = acc;
     }
 }
 
@@ -426,8 +535,11 @@ int forward_impl(const T* value, const int64_t* shapes, const int64_t* lsi, cons
             const int grid = grid_for((n_units + upw - 1) / upw, 8);
             const long long per = (kThreads / 32) * upw;                        // units one CTA pass covers
             const long long upb = ((n_units + grid - 1) / grid + per - 1) / per * per;
-            if (lpu == 8 && L == 4)
+            static const bool use_old = getenv("MDB_MSDA_OLD") != nullptr;     // A/B switch for profiling only
+            if (lpu == 8 && L == 4 && use_old)
                 msda_fwd_vec_kernel<8, 4><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, S, M, L, Lq, n_units, upb, out);
+            else if (lpu == 8 && L == 4)
+                msda_fwd_d32_kernel<<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, S, M, Lq, n_units, upb, out);
             else if (lpu == 8)
                 msda_fwd_vec_kernel<8, 0><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, S, M, L, Lq, n_units, upb, out);
             else if (lpu == 4)
