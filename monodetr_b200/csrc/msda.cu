@@ -175,7 +175,7 @@ __device__ __forceinline__ PointSetup setup_point(float lx_, float ly_, float a,
     return s;
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                     const float* __restrict__ attn, int S, int M, int Lq, long long n_units,
@@ -205,22 +205,20 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
         const int m = (int)(u % M);
         const int b = (int)(u / ((long long)Lq * M));
         const float* vb = value + ((size_t)b * S * M + m) * D + cl * 4;
-        const float2 xyA = __ldg(reinterpret_cast<const float2*>(loc + (size_t)u * (L * P * 2)) + cl);
-        const float2 xyB = __ldg(reinterpret_cast<const float2*>(loc + (size_t)u * (L * P * 2)) + 8 + cl);
-        const float aA = __ldg(attn + (size_t)u * (L * P) + cl), aB = __ldg(attn + (size_t)u * (L * P) + 8 + cl);
-        const PointSetup A = setup_point(xyA.x, xyA.y, aA, HA, WA, sA, pix);
-        const PointSetup Bp = setup_point(xyB.x, xyB.y, aB, HB, WB, sB, pix);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
+#pragma unroll 1
         for (int half = 0; half < 2; ++half) {
-            const PointSetup& Sx = half ? Bp : A;
+            // this lane's point of this half: (l = 2*half + cl/4, p = cl%4)
+            const float2 xy = __ldg(reinterpret_cast<const float2*>(loc + (size_t)u * (L * P * 2)) + half * 8 + cl);
+            const float a = __ldg(attn + (size_t)u * (L * P) + half * 8 + cl);
+            const PointSetup Sx = half ? setup_point(xy.x, xy.y, a, HB, WB, sB, pix) : setup_point(xy.x, xy.y, a, HA, WA, sA, pix);
 #pragma unroll
-            for (int jg = 0; jg < 2; ++jg) {             // 4 points = 16 line loads in flight at a time
-                float4 v[4][4];
-                float w[4][4];
+            for (int jg = 0; jg < 4; ++jg) {             // 2 points = 8 line loads in flight at a time (register budget: 64)
+                float4 v[2][4];
+                float w[2][4];
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const int j = jg * 4 + jj;
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int j = jg * 2 + jj;
                     const int o00 = __shfl_sync(0xffffffffu, Sx.o00, j, 8);
                     const int dxo = __shfl_sync(0xffffffffu, Sx.dxo, j, 8);
                     const int dyo = __shfl_sync(0xffffffffu, Sx.dyo, j, 8);
@@ -233,7 +231,7 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
                     v[jj][3] = ldg4(p00 + dyo + dxo);
                 }
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
+                for (int jj = 0; jj < 2; ++jj) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         acc.x = fmaf(w[jj][k], v[jj][k].x, acc.x);
