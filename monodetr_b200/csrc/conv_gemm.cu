@@ -57,6 +57,7 @@ struct TcParams {
     const float* relu_mask;          // same indexing as out: out *= (mask > 0), or null
     const float* rowscale;           // wgrad: [Mo_rows] or null
     float* out;
+    long long* dbg;                  // profiling aid (tools/diag_timeline.py): clock64 stamps of CTA 0, or null
 };
 
 // Persistent, warp-specialised kernel.  Each CTA walks tiles  tile = blockIdx.x + i * gridDim.x  and keeps
@@ -78,8 +79,11 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     constexpr int kEpiWarp0 = SPLIT ? 6 : 2;                        // first epilogue warp
     static_assert(!(MODE == 1) || B_MN, "wgrad reads both operands MN-major");
 
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // NOTE: index the extern array directly.  Rounding the pointer up through uintptr_t made the compiler lose the
+    // shared address space and emit GENERIC ld/st for every smem access of the splitter and the epilogue (measured:
+    // ~2000 cycles per 32-column epilogue chunk).  The kernel has no static smem, so the dynamic window starts at the
+    // CTA's (1024-byte aligned) shared base; the assumption is checked once below.
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* split_bar = empty_bar + STAGES;                     // splitter warps -> MMA (SPLIT only)
@@ -117,6 +121,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     };
 
     if (threadIdx.x == 0) {
+        if (smem_u32(smem) & 1023u) __trap();                     // SWIZZLE_128B tiles need 1024-byte aligned stages
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapB);
         for (int s = 0; s < STAGES; ++s) {
@@ -146,6 +151,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     const int s = git % STAGES;
                     const uint32_t ph = (git / STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (p.dbg && blockIdx.x == 0 && git < 48) p.dbg[384 + git] = clock64();
                     uint8_t* a_dst = smem + s * kStageBytes;
                     uint8_t* b_dst = a_dst + kTileABytes;
                     mbar_arrive_expect_tx(&full_bar[s], kRawBytes);
@@ -193,8 +199,11 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 const Tile t = decode(tix);
                 if (t.iters == 0) continue;
                 const int slot = lt & 1;
+                const bool dbg = p.dbg && blockIdx.x == 0 && lt < 12;
+                if (dbg) p.dbg[256 + lt * 4 + 0] = clock64();
                 mbar_wait(&tmem_empty[slot], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
                 tc_fence_after();
+                if (dbg) p.dbg[256 + lt * 4 + 1] = clock64();
                 const uint32_t tacc = tmem_base + slot * BN;
                 for (int it = 0; it < t.iters; ++it, ++git) {
                     const int s = git % STAGES;
@@ -224,6 +233,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     umma_commit(&empty_bar[s]);                   // frees the smem stage when these MMAs retire
                 }
                 umma_commit(&tmem_full[slot]);                    // accumulator complete
+                if (dbg) p.dbg[256 + lt * 4 + 2] = clock64();
                 ++lt;
             }
         }
@@ -288,10 +298,13 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 }
             }
             const int slot = lt & 1;
+            const bool dbg = p.dbg && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0 && lt < 12;
+            if (dbg) p.dbg[lt * 16 + 0] = clock64();
             if (t.iters > 0) {
                 mbar_wait(&tmem_full[slot], (lt >> 1) & 1);
                 tc_fence_after();
             }
+            if (dbg) p.dbg[lt * 16 + 1] = clock64();
             const uint32_t taddr_row = tmem_base + slot * BN + ((uint32_t)(q * 32) << 16);
             const float* prow = patch + r4 * kPatchLd + c4 * 4;          // this lane's read window into the transposed patch
 #pragma unroll 1
@@ -324,10 +337,12 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = 0u;
                 }
+                if (dbg && c0 < 128) p.dbg[lt * 16 + 2 + (c0 >> 5) * 3] = clock64();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<uint4*>(patch + lane * kPatchLd + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                 __syncwarp();
+                if (dbg && c0 < 128) p.dbg[lt * 16 + 3 + (c0 >> 5) * 3] = clock64();
                 if (full) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -366,6 +381,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     }
                 }
                 __syncwarp();                  // the patch is rewritten by the next chunk
+                if (dbg && c0 < 128) p.dbg[lt * 16 + 4 + (c0 >> 5) * 3] = clock64();
             }
             if (t.iters > 0) {
                 tc_fence_before();             // TMEM reads of this warp are done: hand the accumulator back
@@ -428,6 +444,7 @@ int make_map(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, 
     return r == CUDA_SUCCESS ? 0 : MDB_EINVAL;
 }
 
+long long* g_dbg = nullptr;   // see mdb_debug_set_timeline
 int g_precision = 1;   // 0 = single-pass TF32 (operands rounded to nearest), 1 = error-compensated 3xTF32 (default)
 
 int num_sms_tc() {
@@ -491,6 +508,8 @@ int check_geom(const ConvGeom& g) {
 
 extern "C" {
 
+void mdb_debug_set_timeline(long long* device_buf) { g_dbg = device_buf; }
+
 int mdb_set_precision(int mode) {
     if (mode != 0 && mode != 1) return MDB_EINVAL;
     g_precision = mode;
@@ -524,7 +543,7 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
         }
     p.wg_taps = 1; p.wg_kw = 1;
     p.No = Cout; p.ldo = Cout; p.relu = flags & 1; p.round_out = (g_precision == 0) ? ((flags >> 1) & 1) : 0; p.atomic_out = 0;
-    p.bias = bias; p.residual = residual; p.relu_mask = nullptr; p.rowscale = nullptr; p.out = y;
+    p.bias = bias; p.residual = residual; p.relu_mask = nullptr; p.rowscale = nullptr; p.out = y; p.dbg = g_dbg;
 
     CUtensorMap ma, mb;
     {   // A: x as (C, W, H, B), box (32, tw*s, th*s, 1), element strides (1, s, s, 1)
