@@ -197,10 +197,11 @@ def run(args, rank, local_rank, ws):
     line = {
         "metric": METRIC, "value": B * ws * args.steps / (total_ms * 1e-3), "unit": "images/sec", "n_gpus": ws,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 storage, " + ("3xTF32 (fp32-equivalent)" if precision == "tf32x3" else "TF32") + " tensor-core math",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == "tf32x3" else "tf32",
         "data": "synthetic",
         "config": {"workload": f"full MonoDETR fwd+bwd, ResNet-50, batch {B}/GPU, 1280x384 synthetic, train mode (550 queries, dropout 0.1), "
-                               f"surrogate loss, {'flat-bucket NCCL all-reduce, ' if ws > 1 else ''}precision={precision}",
+                               f"surrogate loss, {'flat-bucket NCCL all-reduce, ' if ws > 1 else ''}fp32 storage, tensor-core math = "
+                               + ("error-compensated 3xTF32 (fp32-equivalent)" if precision == "tf32x3" else "single-pass TF32"),
                    "parallelism": f"dp{ws}", "global_batch": B * ws,
                    "timing": "CUDA events per step; 256 MiB L2 flush (untimed) between steps; " + ("CUDA graph replay" if graph is not None else "eager launches")},
         "e2e": {"value": B * ws * args.steps / (e2e_ms * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -213,6 +214,9 @@ def run(args, rank, local_rank, ws):
     if enc_ms:
         ach = fwd_bytes / (enc_ms * 1e-3) / 1e9
         line["roofline"] = {"kernel": "msda_fwd_vec_kernel<8> (encoder call, Lq=10200, in situ)", "bound": "hbm", "achieved": ach,
-                            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
+                            "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                            # dram__bytes_read.sum + dram__bytes_write.sum of this launch at B=8 from the committed capture
+                            # profiles/r01_msda_model_r1.txt (239.7 MB + 70.8 MB); scaled with the batch
+                            "traffic": int(310.47e6 * B / 8),
                             "peak_source": pk["source"], "algorithmic_bytes": fwd_bytes, "avg_ms": enc_ms}
     return line

@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/monodetr_b200.h"
@@ -555,7 +556,8 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
         rc = make_map(&ma, x, 4, dims, str, box, es);
         if (rc) return rc;
     }
-    const bool wide = (g_precision == 0) && (Cout >= 256) && ((long long)B * p.tiles_x * p.tiles_y * (Cout / 256) >= 120);
+    static const bool wide_split = getenv("MDB_NO_WIDE_SPLIT") == nullptr;   // A/B switch (profiling)
+    const bool wide = (g_precision == 0 || wide_split) && (Cout % 256 == 0) && ((long long)B * p.tiles_x * p.tiles_y * (Cout / 256) >= 100);
     const int bn = wide ? 256 : (Cout <= 64 ? 64 : 128);
     {   // B: packed weights as (Cin, Cout, taps), box (32, BN, 1)
         uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
@@ -567,6 +569,7 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
     dim3 grid((Cout + bn - 1) / bn, B * p.tiles_x * p.tiles_y, 1);
     if (bn == 64) return (g_precision == 1) ? launch_tc<64, 4, 0, false, true>(ma, mb, p, grid, stream)
                                             : launch_tc<64, 6, 0, false, false>(ma, mb, p, grid, stream);
+    if (g_precision == 1 && wide) return launch_tc<256, 2, 0, false, true>(ma, mb, p, grid, stream);
     if (g_precision == 1) return launch_tc<128, 3, 0, false, true>(ma, mb, p, grid, stream);
     if (wide) return launch_tc<256, 4, 0, false, false>(ma, mb, p, grid, stream);
     return launch_tc<128, 5, 0, false, false>(ma, mb, p, grid, stream);
