@@ -83,20 +83,20 @@ __device__ __forceinline__ void load_afrag(AFrag& f, const float* base, int ld, 
     }
 }
 
+// Streamed tiles are stored PRE-SPLIT in shared memory (hi = rn_tf32(x), lo = rn_tf32(x - hi)) by the loader, once
+// per element, instead of every warp re-splitting every B fragment it reads (3 ALU ops per register per use).
 // C[16 x 64] = A[16 x 32] . S^T, S = smem tile [64][LDS] (rows = the 64 output columns).  NS = 3: error-compensated.
 template <int NS>
-__device__ __forceinline__ void gemm_nt(float (&c)[8][4], const AFrag& a, const float (*s)[LDS], int lane) {
+__device__ __forceinline__ void gemm_nt(float (&c)[8][4], const AFrag& a, const uint32_t (*sh)[LDS], const uint32_t (*sl)[LDS], int lane) {
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
         c[nt][0] = c[nt][1] = c[nt][2] = c[nt][3] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            const float b0f = s[nt * 8 + g][ks * 8 + t], b1f = s[nt * 8 + g][ks * 8 + t + 4];
-            uint32_t b0h, b0l, b1h, b1l;
-            split_tf32(b0f, b0h, b0l);
-            split_tf32(b1f, b1h, b1l);
+            const uint32_t b0h = sh[nt * 8 + g][ks * 8 + t], b1h = sh[nt * 8 + g][ks * 8 + t + 4];
             if (NS == 3) {
+                const uint32_t b0l = sl[nt * 8 + g][ks * 8 + t], b1l = sl[nt * 8 + g][ks * 8 + t + 4];
                 mma8(c[nt], a.lo[ks], b0h, b1h);
                 mma8(c[nt], a.hi[ks], b0l, b1l);
             }
@@ -108,7 +108,7 @@ __device__ __forceinline__ void gemm_nt(float (&c)[8][4], const AFrag& a, const 
 // acc[16 x 32] += P[16 x 64] . S, P given as C fragments (cols 2t,2t+1 of each 8-wide tile), S = smem [64][LDS].
 // k-permutation trick: A col t <-> key 2t, A col t+4 <-> key 2t+1, so A = (c0, c2, c1, c3) and B rows 2t / 2t+1.
 template <int NS>
-__device__ __forceinline__ void gemm_nn(float (&acc)[4][4], const float (&p)[8][4], const float (*s)[LDS], int lane) {
+__device__ __forceinline__ void gemm_nn(float (&acc)[4][4], const float (&p)[8][4], const uint32_t (*sh)[LDS], const uint32_t (*sl)[LDS], int lane) {
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int kt = 0; kt < 8; ++kt) {
@@ -119,11 +119,9 @@ __device__ __forceinline__ void gemm_nn(float (&acc)[4][4], const float (&p)[8][
         split_tf32(p[kt][3], ah[3], al[3]);
 #pragma unroll
         for (int dn = 0; dn < 4; ++dn) {
-            const float b0f = s[kt * 8 + 2 * t][dn * 8 + g], b1f = s[kt * 8 + 2 * t + 1][dn * 8 + g];
-            uint32_t b0h, b0l, b1h, b1l;
-            split_tf32(b0f, b0h, b0l);
-            split_tf32(b1f, b1h, b1l);
+            const uint32_t b0h = sh[kt * 8 + 2 * t][dn * 8 + g], b1h = sh[kt * 8 + 2 * t + 1][dn * 8 + g];
             if (NS == 3) {
+                const uint32_t b0l = sl[kt * 8 + 2 * t][dn * 8 + g], b1l = sl[kt * 8 + 2 * t + 1][dn * 8 + g];
                 mma8(acc[dn], al, b0h, b1h);
                 mma8(acc[dn], ah, b0l, b1l);
             }
@@ -132,13 +130,17 @@ __device__ __forceinline__ void gemm_nn(float (&acc)[4][4], const float (&p)[8][
     }
 }
 
-// cooperative load of a [64][32] tile (rows r0.., zero beyond nrows) into padded smem
-__device__ __forceinline__ void load_tile(float (*s)[LDS], const float* base, int ld, int r0, int nrows) {
+// cooperative load of a [64][32] tile (rows r0.., zero beyond nrows) into padded smem, split into hi (and lo)
+template <bool LO>
+__device__ __forceinline__ void load_tile(uint32_t (*sh)[LDS], uint32_t (*sl)[LDS], const float* base, int ld, int r0, int nrows) {
     for (int i = threadIdx.x; i < BC * (HD / 4); i += ATT_THREADS) {
         const int r = i >> 3, c = (i & 7) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r0 + r < nrows) v = *reinterpret_cast<const float4*>(base + (size_t)(r0 + r) * ld + c);
-        *reinterpret_cast<float4*>(&s[r][c]) = v;
+        uint4 h, l;
+        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+        *reinterpret_cast<uint4*>(&sh[r][c]) = h;
+        if (LO) *reinterpret_cast<uint4*>(&sl[r][c]) = l;
     }
 }
 
@@ -159,8 +161,8 @@ __device__ __forceinline__ float keep_scale(const AttnParams& p, unsigned long l
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_kernel(const AttnParams p) {
-    __shared__ __align__(16) float sK[BC][LDS];
-    __shared__ __align__(16) float sV[BC][LDS];
+    __shared__ __align__(16) uint32_t sKh[BC][LDS], sKl[BC][LDS];
+    __shared__ __align__(16) uint32_t sVh[BC][LDS], sVl[BC][LDS];
     const int b = blockIdx.z, h = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -180,11 +182,11 @@ attn_fwd_kernel(const AttnParams p) {
 
     for (int k0 = 0; k0 < p.Lk; k0 += BC) {
         __syncthreads();
-        load_tile(sK, kb, p.ldk, k0, p.Lk);
-        load_tile(sV, vb, p.ldv, k0, p.Lk);
+        load_tile<true>(sKh, sKl, kb, p.ldk, k0, p.Lk);
+        load_tile<true>(sVh, sVl, vb, p.ldv, k0, p.Lk);
         __syncthreads();
         float s[8][4];
-        gemm_nt<3>(s, qa, sK, lane);
+        gemm_nt<3>(s, qa, sKh, sKl, lane);
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
@@ -218,7 +220,7 @@ attn_fwd_kernel(const AttnParams p) {
             }
         }
         m0 = mn0; m1 = mn1;
-        gemm_nn<3>(acc, s, sV, lane);
+        gemm_nn<3>(acc, s, sVh, sVl, lane);
     }
     l0 = quad_sum(l0); l1 = quad_sum(l1);
     const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
@@ -259,8 +261,8 @@ __global__ void attn_delta_kernel(const AttnParams p) {
 // dQ: CTA = 64 queries, streams key/value tiles.
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dq_kernel(const AttnParams p) {
-    __shared__ __align__(16) float sK[BC][LDS];
-    __shared__ __align__(16) float sV[BC][LDS];
+    __shared__ __align__(16) uint32_t sKh[BC][LDS], sKl[BC][LDS];
+    __shared__ __align__(16) uint32_t sVh[BC][LDS];
     const int b = blockIdx.z, h = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -284,12 +286,12 @@ attn_bwd_dq_kernel(const AttnParams p) {
 
     for (int k0 = 0; k0 < p.Lk; k0 += BC) {
         __syncthreads();
-        load_tile(sK, kb, p.ldk, k0, p.Lk);
-        load_tile(sV, vb, p.ldv, k0, p.Lk);
+        load_tile<true>(sKh, sKl, kb, p.ldk, k0, p.Lk);
+        load_tile<false>(sVh, nullptr, vb, p.ldv, k0, p.Lk);
         __syncthreads();
         float s[8][4], dp[8][4];
-        gemm_nt<3>(s, qa, sK, lane);
-        gemm_nt<1>(dp, ga, sV, lane);          // gradients: single-pass TF32 with round-to-nearest operands
+        gemm_nt<3>(s, qa, sKh, sKl, lane);
+        gemm_nt<1>(dp, ga, sVh, nullptr, lane);   // gradients: single-pass TF32 with round-to-nearest operands
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
@@ -307,7 +309,7 @@ attn_bwd_dq_kernel(const AttnParams p) {
                 s[nt][2 + e] = p1 * (d1 - dl1);
             }
         }
-        gemm_nn<1>(acc, s, sK, lane);
+        gemm_nn<1>(acc, s, sKh, nullptr, lane);
     }
     float* ob = p.dq + (size_t)b * p.Lq * p.lddq + h * HD;
 #pragma unroll
@@ -320,8 +322,8 @@ attn_bwd_dq_kernel(const AttnParams p) {
 // dK / dV: CTA = 64 keys, streams query tiles (Q, dO, lse, delta).
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dkv_kernel(const AttnParams p) {
-    __shared__ __align__(16) float sQ[BC][LDS];
-    __shared__ __align__(16) float sG[BC][LDS];
+    __shared__ __align__(16) uint32_t sQh[BC][LDS], sQl[BC][LDS];
+    __shared__ __align__(16) uint32_t sGh[BC][LDS];
     __shared__ float sL[BC], sD[BC];
     const int b = blockIdx.z, h = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -349,8 +351,8 @@ attn_bwd_dkv_kernel(const AttnParams p) {
 
     for (int q0 = 0; q0 < p.Lq; q0 += BC) {
         __syncthreads();
-        load_tile(sQ, qb, p.ldq, q0, p.Lq);
-        load_tile(sG, gb, p.ldo, q0, p.Lq);
+        load_tile<true>(sQh, sQl, qb, p.ldq, q0, p.Lq);
+        load_tile<false>(sGh, nullptr, gb, p.ldo, q0, p.Lq);
         if (threadIdx.x < BC) {
             const int i = q0 + threadIdx.x;
             sL[threadIdx.x] = i < p.Lq ? p.lse[st + i] : INFINITY;     // +inf -> p = 0 for rows past the end
@@ -358,8 +360,8 @@ attn_bwd_dkv_kernel(const AttnParams p) {
         }
         __syncthreads();
         float s[8][4], dp[8][4];
-        gemm_nt<3>(s, ka, sQ, lane);          // S^T[key][query] (already scaled through K)
-        gemm_nt<1>(dp, va, sG, lane);         // dP^T[key][query] = V . dO^T
+        gemm_nt<3>(s, ka, sQh, sQl, lane);    // S^T[key][query] (already scaled through K)
+        gemm_nt<1>(dp, va, sGh, nullptr, lane);   // dP^T[key][query] = V . dO^T
         float pd[8][4];                        // dropped probabilities for dV
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
@@ -381,8 +383,8 @@ attn_bwd_dkv_kernel(const AttnParams p) {
                 s[nt][2 + e] = p1 * (d1 - dl);
             }
         }
-        gemm_nn<1>(dv, pd, sG, lane);          // dV += P^T_dropped . dO
-        gemm_nn<1>(dk, s, sQ, lane);           // dK += dS^T . Q
+        gemm_nn<1>(dv, pd, sGh, nullptr, lane);   // dV += P^T_dropped . dO
+        gemm_nn<1>(dk, s, sQh, nullptr, lane);    // dK += dS^T . Q
     }
     float* dkb = p.dk + (size_t)b * p.Lk * p.lddk + h * HD;
     float* dvb = p.dv + (size_t)b * p.Lk * p.lddv + h * HD;
