@@ -119,6 +119,7 @@ def run(args, rank, local_rank, ws):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 fwd_bwd()
+            bucket.freeze_sources()
         except Exception as e:          # capture is an optimisation of launch overhead only: same kernels either way
             if rank == 0:
                 print(f"[bench_model] CUDA graph capture failed ({type(e).__name__}: {e}); running eager", flush=True)

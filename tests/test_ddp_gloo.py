@@ -15,7 +15,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, views):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -28,13 +28,13 @@ def _worker(rank, world, port, q):
     })
     broadcast_parameters(model)
     w0 = model["a"].weight.detach().clone()
-    bucket = FlatGradBucket(model)
+    bucket = FlatGradBucket(model, views=views)
     assert bucket.numel == sum(p.numel() for n, p in model.named_parameters() if "sa_v_proj" not in n)
     assert model["sa_v_proj"].weight.grad is None
     bucket.zero()
     x = torch.full((3, 8), float(rank + 1))
-    model["b"](model["a"](x)).sum().backward()   # accumulates straight into the flat views
-    local = bucket.flat.clone()
+    model["b"](model["a"](x)).sum().backward()   # views=True: accumulates straight into the flat views
+    local = torch.cat([p.grad.reshape(-1) for p in bucket.params]).clone()
     assert local.abs().sum() > 0
     bucket.all_reduce()
     gathered = [torch.zeros_like(local) for _ in range(world)]
@@ -45,11 +45,15 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_flat_bucket_allreduce_world2():
+import pytest
+
+
+@pytest.mark.parametrize("views", [False, True])
+def test_flat_bucket_allreduce_world2(views):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, views)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
