@@ -44,29 +44,18 @@ def synthetic_batch(B, seed):
 
 
 class MsdaProbe:
-    """CUDA-event timing of the MSDeformAttn forward launches issued through monodetr_b200.msda (eager steps only)."""
-
-    def __init__(self):
-        self.events = []
+    """CUDA-event timing of the MSDeformAttn forward launches (events recorded immediately around the C call inside
+    monodetr_b200.msda, eager steps only)."""
 
     def __enter__(self):
         from . import msda as _m
         self._m = _m
-        self._orig = _m.ms_deform_attn_forward
-        probe = self
-
-        def timed(value, shapes, lsi, loc, attn, step):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            out = probe._orig(value, shapes, lsi, loc, attn, step)
-            e1.record()
-            probe.events.append((e0, e1, value.shape[0], loc.shape[1]))
-            return out
-        _m.ms_deform_attn_forward = timed
+        self.events = []
+        _m.PROBE = self.events
         return self
 
     def __exit__(self, *a):
-        self._m.ms_deform_attn_forward = self._orig
+        self._m.PROBE = None
 
     def encoder_ms(self):
         ts = [e0.elapsed_time(e1) for e0, e1, _, lq in self.events if lq == FULL_S]

@@ -13,6 +13,9 @@ from torch.autograd.function import once_differentiable
 from . import _lib
 
 
+PROBE = None    # set to a list by bench.py to collect (start_event, stop_event, B, Lq) per forward launch
+
+
 def _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, extra=()):
     tensors = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
                ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), *extra]
@@ -51,8 +54,14 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     out = torch.empty((B, Lq, M * D), dtype=value.dtype, device=value.device)
     fn = _lib.lib().mdb_msda_forward_f32 if value.dtype == torch.float32 else _lib.lib().mdb_msda_forward_f64
     with torch.cuda.device(value.device):
+        if PROBE is not None:       # bench.py: CUDA events tight around the launch (nothing else between them)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = fn(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
                 attn_weight.data_ptr(), B, S, M, D, L, Lq, P, out.data_ptr(), _stream())
+        if PROBE is not None:
+            e1.record()
+            PROBE.append((e0, e1, B, Lq))
     _lib.check(rc, "ms_deform_attn_forward")
     _lib.count(1)
     return out
