@@ -21,6 +21,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "../../include/monodetr_b200.h"
 #include "tc_common.cuh"
 
@@ -345,22 +347,49 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 __syncwarp();
                 if (dbg && c0 < 128) p.dbg[lt * 16 + 3 + (c0 >> 5) * 3] = clock64();
                 if (full) {
+                    // Straight-line, flag-specialised row loop.  With runtime flags inside it the compiler emitted ~66
+                    // dependent instructions per row and, with one epilogue warp per scheduler, each 16 KB chunk took
+                    // ~1900 cycles (profiles/r01_conv_gemm_timeline_cta0.txt); here all 8 patch reads are issued first.
+                    auto rows = [&](auto RES, auto RELU, auto MASK, auto ROUND, auto ATOMIC) {
+                        float4 a[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        if (!((rok >> i) & 1u)) continue;
-                        const float4 a = *reinterpret_cast<const float4*>(prow + i * 4 * kPatchLd);
-                        float4 v = make_float4(fmaf(a.x, rsc[i], bias4.x), fmaf(a.y, rsc[i], bias4.y), fmaf(a.z, rsc[i], bias4.z),
-                                               fmaf(a.w, rsc[i], bias4.w));
-                        if (p.residual) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
-                        if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                        if (p.relu_mask) {
-                            v.x = msk[i].x > 0.f ? v.x : 0.f; v.y = msk[i].y > 0.f ? v.y : 0.f;
-                            v.z = msk[i].z > 0.f ? v.z : 0.f; v.w = msk[i].w > 0.f ? v.w : 0.f;
+                        for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(prow + i * 4 * kPatchLd);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float4 v = make_float4(fmaf(a[i].x, rsc[i], bias4.x), fmaf(a[i].y, rsc[i], bias4.y),
+                                                   fmaf(a[i].z, rsc[i], bias4.z), fmaf(a[i].w, rsc[i], bias4.w));
+                            if constexpr (decltype(RES)::value) { v.x += res[i].x; v.y += res[i].y; v.z += res[i].z; v.w += res[i].w; }
+                            if constexpr (decltype(RELU)::value) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                            if constexpr (decltype(MASK)::value) {
+                                v.x = msk[i].x > 0.f ? v.x : 0.f; v.y = msk[i].y > 0.f ? v.y : 0.f;
+                                v.z = msk[i].z > 0.f ? v.z : 0.f; v.w = msk[i].w > 0.f ? v.w : 0.f;
+                            }
+                            if constexpr (decltype(ROUND)::value) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+                            a[i] = v;
                         }
-                        if (p.round_out) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
-                        float* dst = p.out + roff[i] + n;
-                        if (p.atomic_out) red_add_v4_f32(dst, v.x, v.y, v.z, v.w);
-                        else *reinterpret_cast<float4*>(dst) = v;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if ((rok >> i) & 1u) {
+                                float* dst = p.out + roff[i] + n;
+                                if constexpr (decltype(ATOMIC)::value) red_add_v4_f32(dst, a[i].x, a[i].y, a[i].z, a[i].w);
+                                else *reinterpret_cast<float4*>(dst) = a[i];
+                            }
+                        }
+                    };
+                    using T = std::true_type;
+                    using F = std::false_type;
+                    if (p.atomic_out) rows(F{}, F{}, F{}, F{}, T{});
+                    else if (p.round_out) {       // single-pass TF32 mode only
+                        if (p.residual) { if (p.relu_mask) rows(T{}, F{}, T{}, T{}, F{}); else if (p.relu) rows(T{}, T{}, F{}, T{}, F{}); else rows(T{}, F{}, F{}, T{}, F{}); }
+                        else { if (p.relu_mask) rows(F{}, F{}, T{}, T{}, F{}); else if (p.relu) rows(F{}, T{}, F{}, T{}, F{}); else rows(F{}, F{}, F{}, T{}, F{}); }
+                    } else if (p.residual) {
+                        if (p.relu_mask) rows(T{}, F{}, T{}, F{}, F{});
+                        else if (p.relu) rows(T{}, T{}, F{}, F{}, F{});
+                        else rows(T{}, F{}, F{}, F{}, F{});
+                    } else {
+                        if (p.relu_mask) rows(F{}, F{}, T{}, F{}, F{});
+                        else if (p.relu) rows(F{}, T{}, F{}, F{}, F{});
+                        else rows(F{}, F{}, F{}, F{}, F{});
                     }
                 } else {
                     // ragged right edge (No not a multiple of 32): scalar path, rare (head outputs, padded N)
