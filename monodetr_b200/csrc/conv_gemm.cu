@@ -586,7 +586,10 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
         if (rc) return rc;
     }
     static const bool wide_split = getenv("MDB_NO_WIDE_SPLIT") == nullptr;   // A/B switch (profiling)
-    const bool wide = (g_precision == 0 || wide_split) && (Cout % 256 == 0) && ((long long)B * p.tiles_x * p.tiles_y * (Cout / 256) >= 100);
+    // 3xTF32: a 128x256 tile needs 96 KB per stage -> only 2 stages fit, which cannot hide DRAM latency; it pays off
+    // only when the A operand is re-read from L2 (multi-tap convolutions), measured +6 % on 3x3 256->256.
+    const bool wide = (g_precision == 0 || (wide_split && kh * kw > 1)) && (Cout % 256 == 0) &&
+                      ((long long)B * p.tiles_x * p.tiles_y * (Cout / 256) >= 100);
     const int bn = wide ? 256 : (Cout <= 64 ? 64 : 128);
     {   // B: packed weights as (Cin, Cout, taps), box (32, BN, 1)
         uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
