@@ -155,6 +155,11 @@ int mdb_stem_conv7x7_bn_relu_f32(const float* x, const float* w, const float* sc
 /* torchvision ResNet maxpool(3, 2, 1) on NHWC */
 int mdb_maxpool3x3s2_nhwc_f32(const float* x, float* y, int B, int H, int W, int C, void* stream);
 
+/* Depth-map lookup of the head (monodetr.py:248-253): grid_sample(bilinear, zeros, align_corners=True) of
+ * depth (B,H,W) at xy (B,N,2) in [-1,1] -> out (B,N); backward wrt the map only (centres are detached). */
+int mdb_depth_sample_forward_f32(const float* depth, const float* xy, float* out, int B, int H, int W, int N, void* stream);
+int mdb_depth_sample_backward_f32(const float* dout, const float* xy, float* ddepth, int B, int H, int W, int N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,8 @@ SIGNATURES = {
     "mdb_round_tf32_f32": [_PTR] * 2 + [ctypes.c_longlong, _PTR],
     "mdb_stem_conv7x7_bn_relu_f32": [_PTR] * 5 + [c_int] * 3 + [_PTR],
     "mdb_maxpool3x3s2_nhwc_f32": [_PTR] * 2 + [c_int] * 4 + [_PTR],
+    "mdb_depth_sample_forward_f32": [_PTR] * 3 + [c_int] * 4 + [_PTR],
+    "mdb_depth_sample_backward_f32": [_PTR] * 3 + [c_int] * 4 + [_PTR],
 }
 _RESTYPES = {"mdb_error_string": ctypes.c_char_p}
 

@@ -7,7 +7,7 @@
 //
 // Layout: q[b][i][h][32] with token stride ldq floats (so a packed QKV buffer can be passed), same for
 // k, v (ldk, ldv), out[b][i][h*32] with token stride ldo.  key_padding_mask[b][j] (uint8, nonzero = ignore) or
-// null.  Dropout on the probabilities uses a counter-based hash RNG keyed by (seed, b, h, i, j) so the backward
+// null.  Dropout on the probabilities uses a counter-based hash RNG keyed by (seed, site, b, h, i, j) so the backward
 // pass regenerates the same mask.
 //
 // Mapping: register-resident warp-level tensor-core tiles (mma.sync m16n8k8 TF32, fp32 accumulate).  A CTA of
@@ -130,19 +130,41 @@ __device__ __forceinline__ void gemm_nn(float (&acc)[4][4], const float (&p)[8][
     }
 }
 
-// cooperative load of a [64][32] tile (rows r0.., zero beyond nrows) into padded smem, split into hi (and lo)
-template <bool LO>
-__device__ __forceinline__ void load_tile(uint32_t (*sh)[LDS], uint32_t (*sl)[LDS], const float* base, int ld, int r0, int nrows) {
-    for (int i = threadIdx.x; i < BC * (HD / 4); i += ATT_THREADS) {
+// Streaming of a [64][32] tile is software-pipelined with cp.async: stage_tile issues this thread's four 16-byte
+// asynchronous copies of tile j+1 into a raw staging buffer right before the tensor-core work on tile j; after it,
+// unstage_tile reads the same four slots back (own copies only: cp.async.wait_all suffices, no barrier), splits them
+// into hi (and lo) and writes the padded tiles.  The HBM/L2 latency hides behind the MMAs instead of stalling all
+// four warps at the barrier (long-scoreboard was the top stall of the synchronous version, profiles/r01_attn_fwd_r1.txt)
+// and no registers are held across the MMAs (a register-prefetch variant cost 57-80 registers and a CTA per SM).
+constexpr int STG = BC * HD;       // floats per staging buffer
+__device__ __forceinline__ void stage_tile(float* stg, const float* base, int ld, int r0, int nrows) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = threadIdx.x + u * ATT_THREADS;
         const int r = i >> 3, c = (i & 7) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r0 + r < nrows) v = *reinterpret_cast<const float4*>(base + (size_t)(r0 + r) * ld + c);
+        const bool ok = r0 + r < nrows;
+        const float* src = ok ? base + ((size_t)(r0 + r) * ld + c) : base;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(stg) + (uint32_t)i * 16u;
+        const int nbytes = ok ? 16 : 0;                              // 0 -> the 16 bytes are zero-filled
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+    }
+}
+__device__ __forceinline__ void stage_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <bool LO>
+__device__ __forceinline__ void unstage_tile(uint32_t (*sh)[LDS], uint32_t (*sl)[LDS], const float* stg) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = threadIdx.x + u * ATT_THREADS;
+        const int r = i >> 3, c = (i & 7) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(stg + i * 4);
         uint4 h, l;
         split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
         *reinterpret_cast<uint4*>(&sh[r][c]) = h;
         if (LO) *reinterpret_cast<uint4*>(&sl[r][c]) = l;
     }
 }
+static_assert(BC * (HD / 4) == 4 * ATT_THREADS, "tile loader mapping");
 
 __device__ __forceinline__ float quad_max(float v) {
     v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
@@ -153,16 +175,45 @@ __device__ __forceinline__ float quad_sum(float v) {
     return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 
-__device__ __forceinline__ float keep_scale(const AttnParams& p, unsigned long long seed, int b, int h, int i, int j, float inv_keep) {
-    const unsigned long long idx = (((unsigned long long)(b * p.H + h) * p.Lq + i) * (unsigned long long)p.Lk + j);
-    return mdb::rng_uniform(seed, idx) >= p.drop_p ? inv_keep : 0.f;
+// Dropout on the probabilities: keep(b, h, i, j) = fmix32-hash of (i * Lk + j) keyed per (seed, site, b, h); the
+// same pure function in all three kernels.  Host check: Lq * Lk < 2^32.
+struct DropCtx {
+    uint32_t key, thr;
+    float inv_keep;
+    bool on;
+};
+__device__ __forceinline__ DropCtx make_drop(const AttnParams& p, int b, int h) {
+    DropCtx d;
+    d.on = p.drop_p > 0.f;
+    d.inv_keep = 1.f / (1.f - p.drop_p);
+    d.thr = (uint32_t)fminf(p.drop_p * 4294967296.f, 4294967040.f);
+    d.key = 0u;
+    if (d.on) d.key = mdb::rng_key32(*p.seed + p.site * 0x9E3779B97F4A7C15ull, (unsigned long long)(b * p.H + h));
+    return d;
+}
+__device__ __forceinline__ float keep_scale(const DropCtx& d, uint32_t row_base, int j) {   // row_base = i * Lk
+    return mdb::rng_keep32(d.key, row_base + (uint32_t)j, d.thr) ? d.inv_keep : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ATT_THREADS)
+// dead-key flags of the streamed tile (key_padding_mask or past the end), fetched with the tile and read from smem
+__device__ __forceinline__ uint32_t fetch_dead(const AttnParams& p, int b, int k0) {
+    const int j = k0 + (int)threadIdx.x;
+    if (threadIdx.x >= BC) return 0u;
+    if (j >= p.Lk) return 1u;
+    return (p.kpm && p.kpm[(size_t)b * p.Lk + j]) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 4)
 attn_fwd_kernel(const AttnParams p) {
-    __shared__ __align__(16) uint32_t sKh[BC][LDS], sKl[BC][LDS];
-    __shared__ __align__(16) uint32_t sVh[BC][LDS], sVl[BC][LDS];
+    extern __shared__ __align__(16) uint8_t dyn_smem[];             // kFwdSmem bytes: 4 padded tiles, 2 staging buffers, flags
+    uint32_t (*sKh)[LDS] = reinterpret_cast<uint32_t (*)[LDS]>(dyn_smem);
+    uint32_t (*sKl)[LDS] = sKh + BC;
+    uint32_t (*sVh)[LDS] = sKl + BC;
+    uint32_t (*sVl)[LDS] = sVh + BC;
+    float* gK = reinterpret_cast<float*>(sVl + BC);
+    float* gV = gK + STG;
+    uint8_t* sDead = reinterpret_cast<uint8_t*>(gV + STG);
     const int b = blockIdx.z, h = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -170,8 +221,11 @@ attn_fwd_kernel(const AttnParams p) {
     const float* qb = p.q + (size_t)b * p.Lq * p.ldq + h * HD;
     const float* kb = p.k + (size_t)b * p.Lk * p.ldk + h * HD;
     const float* vb = p.v + (size_t)b * p.Lk * p.ldv + h * HD;
-    const unsigned long long seed = (p.drop_p > 0.f) ? (*p.seed + p.site * 0x9E3779B97F4A7C15ull) : 0ull;
-    const float inv_keep = 1.f / (1.f - p.drop_p);
+    const DropCtx drop = make_drop(p, b, h);
+    stage_tile(gK, kb, p.ldk, 0, p.Lk);
+    stage_tile(gV, vb, p.ldv, 0, p.Lk);
+    stage_commit();
+    uint32_t ndead = fetch_dead(p, b, 0);
     AFrag qa;
     load_afrag(qa, qb, p.ldq, r0, p.Lq, lane, p.scale);
     float acc[4][4];
@@ -179,25 +233,31 @@ attn_fwd_kernel(const AttnParams p) {
     for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;      // rows g and g+8
     const int qi0 = r0 + g, qi1 = r0 + g + 8;
+    const uint32_t rb0 = (uint32_t)qi0 * (uint32_t)p.Lk, rb1 = (uint32_t)qi1 * (uint32_t)p.Lk;
 
     for (int k0 = 0; k0 < p.Lk; k0 += BC) {
+        stage_wait();
+        __syncthreads();                       // every warp is done with the previous tiles
+        unstage_tile<true>(sKh, sKl, gK);
+        unstage_tile<true>(sVh, sVl, gV);
+        if (threadIdx.x < BC) sDead[threadIdx.x] = (uint8_t)ndead;
         __syncthreads();
-        load_tile<true>(sKh, sKl, kb, p.ldk, k0, p.Lk);
-        load_tile<true>(sVh, sVl, vb, p.ldv, k0, p.Lk);
-        __syncthreads();
+        if (k0 + BC < p.Lk) {                  // next tile's copies fly during this tile's MMAs
+            stage_tile(gK, kb, p.ldk, k0 + BC, p.Lk);
+            stage_tile(gV, vb, p.ldv, k0 + BC, p.Lk);
+            stage_commit();
+            ndead = fetch_dead(p, b, k0 + BC);
+        }
         float s[8][4];
         gemm_nt<3>(s, qa, sKh, sKl, lane);
         float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int j = k0 + nt * 8 + 2 * t + e;
-                const bool dead = (j >= p.Lk) || (p.kpm && p.kpm[(size_t)b * p.Lk + min(j, p.Lk - 1)]);
-                if (dead) { s[nt][e] = -INFINITY; s[nt][2 + e] = -INFINITY; }
-                mx0 = fmaxf(mx0, s[nt][e]);
-                mx1 = fmaxf(mx1, s[nt][2 + e]);
-            }
+            const uchar2 dd = *reinterpret_cast<const uchar2*>(&sDead[nt * 8 + 2 * t]);
+            if (dd.x) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+            if (dd.y) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+            mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
         }
         const float mn0 = fmaxf(m0, quad_max(mx0)), mn1 = fmaxf(m1, quad_max(mx1));
         const float c0 = (mn0 == -INFINITY) ? 1.f : __expf(m0 - mn0), c1 = (mn1 == -INFINITY) ? 1.f : __expf(m1 - mn1);
@@ -212,9 +272,9 @@ attn_fwd_kernel(const AttnParams p) {
                 float p0 = (mn0 == -INFINITY) ? 0.f : __expf(s[nt][e] - mn0);
                 float p1 = (mn1 == -INFINITY) ? 0.f : __expf(s[nt][2 + e] - mn1);
                 l0 += p0; l1 += p1;
-                if (p.drop_p > 0.f) {
-                    p0 *= keep_scale(p, seed, b, h, qi0, j, inv_keep);
-                    p1 *= keep_scale(p, seed, b, h, qi1, j, inv_keep);
+                if (drop.on) {
+                    p0 *= keep_scale(drop, rb0, j);
+                    p1 *= keep_scale(drop, rb1, j);
                 }
                 s[nt][e] = p0; s[nt][2 + e] = p1;
             }
@@ -259,10 +319,12 @@ __global__ void attn_delta_kernel(const AttnParams p) {
 }
 
 // dQ: CTA = 64 queries, streams key/value tiles.
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(ATT_THREADS, 3)
 attn_bwd_dq_kernel(const AttnParams p) {
     __shared__ __align__(16) uint32_t sKh[BC][LDS], sKl[BC][LDS];
     __shared__ __align__(16) uint32_t sVh[BC][LDS];
+    __shared__ __align__(16) float gK[STG], gV[STG];
+    __shared__ __align__(8) uint8_t sDead[BC];
     const int b = blockIdx.z, h = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -271,39 +333,55 @@ attn_bwd_dq_kernel(const AttnParams p) {
     const float* gb = p.dout + (size_t)b * p.Lq * p.ldo + h * HD;
     const float* kb = p.k + (size_t)b * p.Lk * p.ldk + h * HD;
     const float* vb = p.v + (size_t)b * p.Lk * p.ldv + h * HD;
-    const unsigned long long seed = (p.drop_p > 0.f) ? (*p.seed + p.site * 0x9E3779B97F4A7C15ull) : 0ull;
-    const float inv_keep = 1.f / (1.f - p.drop_p);
+    const DropCtx drop = make_drop(p, b, h);
+    stage_tile(gK, kb, p.ldk, 0, p.Lk);
+    stage_tile(gV, vb, p.ldv, 0, p.Lk);
+    stage_commit();
+    uint32_t ndead = fetch_dead(p, b, 0);
     AFrag qa, ga;
     load_afrag(qa, qb, p.ldq, r0, p.Lq, lane, p.scale);
     load_afrag(ga, gb, p.ldo, r0, p.Lq, lane, 1.f);
     const int qi0 = r0 + g, qi1 = r0 + g + 8;
+    const uint32_t rb0 = (uint32_t)qi0 * (uint32_t)p.Lk, rb1 = (uint32_t)qi1 * (uint32_t)p.Lk;
     const size_t st = ((size_t)b * p.H + h) * p.Lq;
-    const float lse0 = qi0 < p.Lq ? p.lse[st + qi0] : INFINITY, lse1 = qi1 < p.Lq ? p.lse[st + qi1] : INFINITY;
+    // lse = -inf (fully masked row) or a row past the end: +inf makes every p = exp(s - lse) exactly 0
+    float lse0 = qi0 < p.Lq ? p.lse[st + qi0] : INFINITY, lse1 = qi1 < p.Lq ? p.lse[st + qi1] : INFINITY;
+    if (lse0 == -INFINITY) lse0 = INFINITY;
+    if (lse1 == -INFINITY) lse1 = INFINITY;
     const float dl0 = qi0 < p.Lq ? p.delta[st + qi0] : 0.f, dl1 = qi1 < p.Lq ? p.delta[st + qi1] : 0.f;
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 
     for (int k0 = 0; k0 < p.Lk; k0 += BC) {
+        stage_wait();
         __syncthreads();
-        load_tile<true>(sKh, sKl, kb, p.ldk, k0, p.Lk);
-        load_tile<false>(sVh, nullptr, vb, p.ldv, k0, p.Lk);
+        unstage_tile<true>(sKh, sKl, gK);
+        unstage_tile<false>(sVh, nullptr, gV);
+        if (threadIdx.x < BC) sDead[threadIdx.x] = (uint8_t)ndead;
         __syncthreads();
+        if (k0 + BC < p.Lk) {
+            stage_tile(gK, kb, p.ldk, k0 + BC, p.Lk);
+            stage_tile(gV, vb, p.ldv, k0 + BC, p.Lk);
+            stage_commit();
+            ndead = fetch_dead(p, b, k0 + BC);
+        }
         float s[8][4], dp[8][4];
         gemm_nt<3>(s, qa, sKh, sKl, lane);
         gemm_nt<1>(dp, ga, sVh, nullptr, lane);   // gradients: single-pass TF32 with round-to-nearest operands
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
+            const uchar2 dd = *reinterpret_cast<const uchar2*>(&sDead[nt * 8 + 2 * t]);
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int j = k0 + nt * 8 + 2 * t + e;
-                const bool dead = (j >= p.Lk) || (p.kpm && p.kpm[(size_t)b * p.Lk + min(j, p.Lk - 1)]);
-                float p0 = (dead || lse0 == -INFINITY) ? 0.f : __expf(s[nt][e] - lse0);
-                float p1 = (dead || lse1 == -INFINITY) ? 0.f : __expf(s[nt][2 + e] - lse1);
+                const bool dead = e ? dd.y : dd.x;
+                float p0 = dead ? 0.f : __expf(s[nt][e] - lse0);
+                float p1 = dead ? 0.f : __expf(s[nt][2 + e] - lse1);
                 float d0 = dp[nt][e], d1 = dp[nt][2 + e];
-                if (p.drop_p > 0.f) {
-                    d0 *= keep_scale(p, seed, b, h, qi0, j, inv_keep);
-                    d1 *= keep_scale(p, seed, b, h, qi1, j, inv_keep);
+                if (drop.on) {
+                    d0 *= keep_scale(drop, rb0, j);
+                    d1 *= keep_scale(drop, rb1, j);
                 }
                 s[nt][e] = p0 * (d0 - dl0);
                 s[nt][2 + e] = p1 * (d1 - dl1);
@@ -320,11 +398,12 @@ attn_bwd_dq_kernel(const AttnParams p) {
 }
 
 // dK / dV: CTA = 64 keys, streams query tiles (Q, dO, lse, delta).
-__global__ void __launch_bounds__(ATT_THREADS)
+__global__ void __launch_bounds__(ATT_THREADS, 3)
 attn_bwd_dkv_kernel(const AttnParams p) {
     __shared__ __align__(16) uint32_t sQh[BC][LDS], sQl[BC][LDS];
     __shared__ __align__(16) uint32_t sGh[BC][LDS];
-    __shared__ float sL[BC], sD[BC];
+    __shared__ __align__(16) float gQ[STG], gG[STG];
+    __shared__ __align__(8) float sL[BC], sD[BC];
     const int b = blockIdx.z, h = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -333,8 +412,23 @@ attn_bwd_dkv_kernel(const AttnParams p) {
     const float* gb = p.dout + (size_t)b * p.Lq * p.ldo + h * HD;
     const float* kb = p.k + (size_t)b * p.Lk * p.ldk + h * HD;
     const float* vb = p.v + (size_t)b * p.Lk * p.ldv + h * HD;
-    const unsigned long long seed = (p.drop_p > 0.f) ? (*p.seed + p.site * 0x9E3779B97F4A7C15ull) : 0ull;
-    const float inv_keep = 1.f / (1.f - p.drop_p);
+    const DropCtx drop = make_drop(p, b, h);
+    const size_t st = ((size_t)b * p.H + h) * p.Lq;
+    // per-thread row statistics of the streamed query tile (threads 0..63): lse (+inf -> p = 0) and delta
+    auto fetch_stats = [&](int q0, float& l, float& d) {
+        const int i = q0 + (int)threadIdx.x;
+        l = INFINITY; d = 0.f;
+        if (threadIdx.x < BC && i < p.Lq) {
+            l = p.lse[st + i];
+            d = p.delta[st + i];
+            if (l == -INFINITY) l = INFINITY;
+        }
+    };
+    float nl, nd;
+    stage_tile(gQ, qb, p.ldq, 0, p.Lq);
+    stage_tile(gG, gb, p.ldo, 0, p.Lq);
+    stage_commit();
+    fetch_stats(0, nl, nd);
     AFrag ka, va;
     load_afrag(ka, kb, p.ldk, r0, p.Lk, lane, p.scale);
     load_afrag(va, vb, p.ldv, r0, p.Lk, lane, 1.f);
@@ -347,35 +441,39 @@ attn_bwd_dkv_kernel(const AttnParams p) {
         dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
         dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
     }
-    const size_t st = ((size_t)b * p.H + h) * p.Lq;
 
     for (int q0 = 0; q0 < p.Lq; q0 += BC) {
+        stage_wait();
         __syncthreads();
-        load_tile<true>(sQh, sQl, qb, p.ldq, q0, p.Lq);
-        load_tile<false>(sGh, nullptr, gb, p.ldo, q0, p.Lq);
-        if (threadIdx.x < BC) {
-            const int i = q0 + threadIdx.x;
-            sL[threadIdx.x] = i < p.Lq ? p.lse[st + i] : INFINITY;     // +inf -> p = 0 for rows past the end
-            sD[threadIdx.x] = i < p.Lq ? p.delta[st + i] : 0.f;
+        unstage_tile<true>(sQh, sQl, gQ);
+        unstage_tile<false>(sGh, nullptr, gG);
+        if (threadIdx.x < BC) { sL[threadIdx.x] = nl; sD[threadIdx.x] = nd; }
+        __syncthreads();
+        if (q0 + BC < p.Lq) {
+            stage_tile(gQ, qb, p.ldq, q0 + BC, p.Lq);
+            stage_tile(gG, gb, p.ldo, q0 + BC, p.Lq);
+            stage_commit();
+            fetch_stats(q0 + BC, nl, nd);
         }
-        __syncthreads();
         float s[8][4], dp[8][4];
         gemm_nt<3>(s, ka, sQh, sQl, lane);    // S^T[key][query] (already scaled through K)
         gemm_nt<1>(dp, va, sGh, nullptr, lane);   // dP^T[key][query] = V . dO^T
         float pd[8][4];                        // dropped probabilities for dV
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt) {
+            const float2 l2 = *reinterpret_cast<const float2*>(&sL[nt * 8 + 2 * t]);
+            const float2 d2 = *reinterpret_cast<const float2*>(&sD[nt * 8 + 2 * t]);
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int il = nt * 8 + 2 * t + e, i = q0 + il;
-                const float lse = sL[il], dl = sD[il];
-                const bool nolse = (lse == -INFINITY);
-                float p0 = (dead0 || nolse) ? 0.f : __expf(s[nt][e] - lse);
-                float p1 = (dead1 || nolse) ? 0.f : __expf(s[nt][2 + e] - lse);
+                const int i = q0 + nt * 8 + 2 * t + e;
+                const float lse = e ? l2.y : l2.x, dl = e ? d2.y : d2.x;
+                float p0 = dead0 ? 0.f : __expf(s[nt][e] - lse);
+                float p1 = dead1 ? 0.f : __expf(s[nt][2 + e] - lse);
                 float d0 = dp[nt][e], d1 = dp[nt][2 + e];
                 float w0 = p0, w1 = p1;
-                if (p.drop_p > 0.f) {
-                    const float k0s = keep_scale(p, seed, b, h, i, kj0, inv_keep), k1s = keep_scale(p, seed, b, h, i, kj1, inv_keep);
+                if (drop.on) {
+                    const uint32_t rb = (uint32_t)i * (uint32_t)p.Lk;
+                    const float k0s = keep_scale(drop, rb, kj0), k1s = keep_scale(drop, rb, kj1);
                     w0 *= k0s; w1 *= k1s; d0 *= k0s; d1 *= k1s;
                 }
                 pd[nt][e] = w0; pd[nt][2 + e] = w1;
@@ -407,6 +505,7 @@ int check(const AttnParams& p) {
     if (p.drop_p < 0.f || p.drop_p >= 1.f) return MDB_EINVAL;
     if (p.drop_p > 0.f && !p.seed) return MDB_EINVAL;
     if (p.H > 65535 || p.B > 65535) return MDB_EUNSUPPORTED;
+    if ((unsigned long long)p.Lq * (unsigned long long)p.Lk >= (1ull << 32)) return MDB_EUNSUPPORTED;   // 32-bit mask index
     return 0;
 }
 
@@ -427,7 +526,14 @@ int mdb_attention_forward_f32(const float* q, const float* k, const float* v, co
     int rc = check(p);
     if (rc) return rc;
     dim3 grid((Lq + BR - 1) / BR, H, B);
-    attn_fwd_kernel<<<grid, ATT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    constexpr int kFwdSmem = 4 * BC * LDS * 4 + 2 * STG * 4 + BC;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    attn_fwd_kernel<<<grid, ATT_THREADS, kFwdSmem, static_cast<cudaStream_t>(stream)>>>(p);
     return (int)cudaGetLastError();
 }
 

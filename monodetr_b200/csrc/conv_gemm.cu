@@ -314,7 +314,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 if (t.n0 + c0 >= p.No) break;  // uniform across the CTA
                 const int n = t.n0 + c0 + c4 * 4;
-                const bool full = (t.n0 + c0 + 32 <= p.No);             // uniform: every lane's float4 is in range
+                const bool full = (t.n0 + c0 + 32 <= p.No) && !(p.ldo & 3);   // uniform: every lane's float4 is in range and 16B aligned
                 // Issue the global reads of this chunk (residual / ReLU mask / bias, read-only path) BEFORE waiting on
                 // TMEM so their latency overlaps; the two flags are uniform, the bodies are specialised below.
                 float4 res[8], msk[8];
@@ -527,10 +527,12 @@ struct ConvGeom {
     int B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo;
 };
 
-int check_geom(const ConvGeom& g) {
+int check_geom(const ConvGeom& g, bool forward = false) {
     if (g.B <= 0 || g.H <= 0 || g.W <= 0 || g.Cin <= 0 || g.Cout <= 0) return MDB_EINVAL;
     if (g.kh != g.kw || (g.kh != 1 && g.kh != 3) || (g.stride != 1 && g.stride != 2)) return MDB_EUNSUPPORTED;
-    if (g.Cin % 4 || g.Cout % 4) return MDB_EUNSUPPORTED;
+    // TMA needs 16-byte row pitches on every operand it reads: Cin always; Cout only where dy / the output map is an
+    // operand (dgrad, wgrad).  The forward epilogue writes ragged Cout with scalar stores.
+    if (g.Cin % 4 || (!forward && g.Cout % 4)) return MDB_EUNSUPPORTED;
     return 0;
 }
 
@@ -552,7 +554,7 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
                            int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int flags,
                            void* stream_) {
     ConvGeom g{B, H, W, Cin, Cout, kh, kw, stride, pad, (H + 2 * pad - kh) / stride + 1, (W + 2 * pad - kw) / stride + 1};
-    int rc = check_geom(g);
+    int rc = check_geom(g, true);
     if (rc) return rc;
     if (!x || !w_packed || !y) return MDB_EINVAL;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -305,3 +305,63 @@ int mdb_maxpool3x3s2_nhwc_f32(const float* x, float* y, int B, int H, int W, int
 }
 
 }  // extern "C"
+
+// =================================================================================================
+// Depth-map lookup of the detection head (monodetr.py:248-253): F.grid_sample(weighted_depth[:, None], centres,
+// bilinear, zeros padding, align_corners=True) for N query centres per image, forward and backward wrt the map
+// (the centres are detached in the reference).  One thread per (b, n).
+// =================================================================================================
+namespace {
+
+__global__ void depth_sample_fwd_kernel(const float* __restrict__ depth, const float* __restrict__ xy, float* __restrict__ out,
+                                        int B, int H, int W, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * N) return;
+    const int b = i / N;
+    const float x = (xy[2 * i] + 1.f) * 0.5f * (float)(W - 1), y = (xy[2 * i + 1] + 1.f) * 0.5f * (float)(H - 1);
+    const float xf = floorf(x), yf = floorf(y);
+    const int x0 = (int)xf, y0 = (int)yf;
+    const float lx = x - xf, ly = y - yf;
+    const float* d = depth + (size_t)b * H * W;
+    auto tap = [&](int yy, int xx) { return (xx >= 0 && xx <= W - 1 && yy >= 0 && yy <= H - 1) ? d[yy * W + xx] : 0.f; };
+    out[i] = tap(y0, x0) * (1.f - ly) * (1.f - lx) + tap(y0, x0 + 1) * (1.f - ly) * lx + tap(y0 + 1, x0) * ly * (1.f - lx) +
+             tap(y0 + 1, x0 + 1) * ly * lx;
+}
+
+__global__ void depth_sample_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ xy, float* __restrict__ ddepth,
+                                        int B, int H, int W, int N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * N) return;
+    const int b = i / N;
+    const float x = (xy[2 * i] + 1.f) * 0.5f * (float)(W - 1), y = (xy[2 * i + 1] + 1.f) * 0.5f * (float)(H - 1);
+    const float xf = floorf(x), yf = floorf(y);
+    const int x0 = (int)xf, y0 = (int)yf;
+    const float lx = x - xf, ly = y - yf, g = dout[i];
+    float* d = ddepth + (size_t)b * H * W;
+    auto put = [&](int yy, int xx, float w) { if (xx >= 0 && xx <= W - 1 && yy >= 0 && yy <= H - 1) atomicAdd(d + yy * W + xx, w * g); };
+    put(y0, x0, (1.f - ly) * (1.f - lx)); put(y0, x0 + 1, (1.f - ly) * lx); put(y0 + 1, x0, ly * (1.f - lx)); put(y0 + 1, x0 + 1, ly * lx);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mdb_depth_sample_forward_f32(const float* depth, const float* xy, float* out, int B, int H, int W, int N, void* stream) {
+    if (!depth || !xy || !out || B <= 0 || H <= 0 || W <= 0 || N < 0) return MDB_EINVAL;
+    if (N == 0) return 0;
+    depth_sample_fwd_kernel<<<(B * N + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(depth, xy, out, B, H, W, N);
+    return (int)cudaGetLastError();
+}
+
+// ddepth (B,H,W) is zero-filled by the call, then accumulated.
+int mdb_depth_sample_backward_f32(const float* dout, const float* xy, float* ddepth, int B, int H, int W, int N, void* stream_) {
+    if (!dout || !xy || !ddepth || B <= 0 || H <= 0 || W <= 0 || N < 0) return MDB_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    cudaError_t e = cudaMemsetAsync(ddepth, 0, sizeof(float) * (size_t)B * H * W, stream);
+    if (e != cudaSuccess) return (int)e;
+    if (N == 0) return 0;
+    depth_sample_bwd_kernel<<<(B * N + 127) / 128, 128, 0, stream>>>(dout, xy, ddepth, B, H, W, N);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -30,4 +30,22 @@ __host__ __device__ __forceinline__ void rng_uniform4(uint64_t seed, uint64_t qu
     u[3] = (float)(uint32_t)((h >> 48) & 0xFFFF) * (1.0f / 65536.0f);
 }
 
+// 32-bit variant for per-element masks inside tight loops (attention probabilities): key = one 64-bit hash per
+// (seed, site, batch*head) computed once per CTA, then ~10 integer instructions per element.  idx < 2^32.
+__host__ __device__ __forceinline__ uint32_t fmix32(uint32_t x) {   // MurmurHash3 32-bit finalizer
+    x ^= x >> 16;
+    x *= 0x85ebca6bu;
+    x ^= x >> 13;
+    x *= 0xc2b2ae35u;
+    x ^= x >> 16;
+    return x;
+}
+__host__ __device__ __forceinline__ uint32_t rng_key32(uint64_t seed, uint64_t stream) {
+    return (uint32_t)(fmix64(stream * 0x9E3779B97F4A7C15ull + seed) >> 17);
+}
+// true with probability 1 - thr / 2^32
+__host__ __device__ __forceinline__ bool rng_keep32(uint32_t key, uint32_t idx, uint32_t thr) {
+    return fmix32(idx * 0x9E3779B1u + key) >= thr;
+}
+
 }  // namespace mdb

@@ -73,31 +73,28 @@ class _Linear(Function):
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         wr = tc.round_tf32(w.contiguous())
-        bp = b
-        if Np != N:
-            wr = F.pad(wr, (0, 0, 0, Np - N))
-            bp = None if b is None else F.pad(b, (0, Np - N))
         r2 = None
         if residual is not None:
-            assert Np == N
             r2 = residual.reshape(-1, N).contiguous()
-        y = tc.linear_forward(x2, wr, None if bp is None else bp.contiguous(), r2, relu=relu)
+        # the forward kernel takes any N (ragged right edge handled in its epilogue); only the backward operands need
+        # 16-byte row pitches, so padding to a multiple of 4 happens there
+        y = tc.linear_forward(x2, wr, None if b is None else b.contiguous(), r2, relu=relu)
         ctx.save_for_backward(x2, wr, y if relu else None)
         ctx.meta = (x.shape, N, Np, b is not None, residual is not None, relu)
-        out = y if Np == N else y[:, :N].contiguous()
-        return out.view(*x.shape[:-1], N)
+        return y.view(*x.shape[:-1], N)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
         x2, wr, y = ctx.saved_tensors
         xshape, N, Np, has_b, has_res, relu = ctx.meta
-        dy2 = dy.reshape(-1, N)
+        dy2 = dy.reshape(-1, N).contiguous()
+        if relu:
+            dy2 = relu_backward(dy2, y) if N % 4 == 0 else dy2 * (y > 0)
+        dres_src = dy2
         if Np != N:
             dy2 = F.pad(dy2, (0, Np - N))
-        dy2 = dy2.contiguous()
-        if relu:
-            dy2 = relu_backward(dy2, y)
+            wr = F.pad(wr, (0, 0, 0, Np - N))
         dx = dw = db = dres = None
         if ctx.needs_input_grad[0]:
             dx = tc.linear_dgrad(dy2, wr).view(xshape)
@@ -110,7 +107,7 @@ class _Linear(Function):
             if Np != N:
                 db = db[:N]
         if has_res and ctx.needs_input_grad[3]:
-            dres = dy2.view(*xshape[:-1], N)
+            dres = dres_src.view(*xshape[:-1], N)
         return dx, dw, db, dres, None
 
 
@@ -275,3 +272,34 @@ class _MsdaPrep(Function):
 
 def msda_prep(off, logits, ref, spatial_shapes, M, L, P):
     return _MsdaPrep.apply(off, logits, ref, spatial_shapes, M, L, P)
+
+
+class _DepthSample(Function):
+    """grid_sample(depth[:, None], xy[:, :, None], bilinear, zeros, align_corners=True) -> (B, N); xy is not differentiated."""
+
+    @staticmethod
+    def forward(ctx, depth, xy):
+        depth = depth.contiguous()
+        xy = xy.detach().contiguous()
+        B, H, W = depth.shape
+        N = xy.shape[1]
+        out = torch.empty((B, N), dtype=torch.float32, device=depth.device)
+        _lib.check(_lib.lib().mdb_depth_sample_forward_f32(_p(depth), _p(xy), _p(out), B, H, W, N, _s()), "depth_sample_forward")
+        _lib.count(1)
+        ctx.save_for_backward(xy)
+        ctx.meta = (B, H, W, N)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        (xy,) = ctx.saved_tensors
+        B, H, W, N = ctx.meta
+        dd = torch.empty((B, H, W), dtype=torch.float32, device=dout.device)
+        _lib.check(_lib.lib().mdb_depth_sample_backward_f32(_p(dout.contiguous()), _p(xy), _p(dd), B, H, W, N, _s()), "depth_sample_backward")
+        _lib.count(1)
+        return dd, None
+
+
+def depth_sample(depth, xy):
+    return _DepthSample.apply(depth, xy)

@@ -136,7 +136,7 @@ class MonoDETR(nn.Module):
             depth_geo = size3d[:, :, 0] / box2d_height * calibs[:, 0, 0].unsqueeze(1)
             depth_reg = self.depth_embed[lvl](hs[lvl])
             outputs_center3d = ((outputs_coord[..., :2] - 0.5) * 2).detach()
-            depth_map = bilinear_sample_align_corners(weighted_depth, outputs_center3d).unsqueeze(-1)
+            depth_map = Fn.depth_sample(weighted_depth, outputs_center3d).unsqueeze(-1)
             depth_ave = torch.cat([((1. / (depth_reg[:, :, 0:1].sigmoid() + 1e-6) - 1.) + depth_geo.unsqueeze(-1) + depth_map) / 3,
                                    depth_reg[:, :, 1:2]], -1)
             outputs_depths.append(depth_ave)

@@ -38,7 +38,8 @@ def _report(name, a, b):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 256), (1000, 256, 256), (10200, 256, 256), (4400, 128, 256),
-                                   (333, 24, 256), (550, 4, 256), (81600, 256, 256), (2048, 1024, 512), (777, 512, 2048)])
+                                   (333, 24, 256), (550, 4, 256), (81600, 256, 256), (2048, 1024, 512), (777, 512, 2048),
+                                   (550, 3, 256), (550, 6, 256), (4400, 81, 256), (129, 1, 64), (300, 35, 128)])
 def test_linear_forward(M, N, K):
     from monodetr_b200 import tc
     _ref_setup()
@@ -125,3 +126,32 @@ def test_conv_forward_backward(cfg):
     dwp = tc.conv2d_wgrad(dy_nhwc, x_nhwc, scale, k, k, s, pad)
     dw = tc.unpack_wgrad(dwp, k, k)
     assert _report("wgrad", dw, wr.grad * scale.view(-1, 1, 1, 1)) < TOL
+
+
+@pytest.mark.parametrize("M,N,K,relu", [(550, 3, 256, False), (4400, 81, 256, True), (1000, 6, 256, False), (640, 256, 256, True)])
+def test_functional_linear_autograd_ragged_n(M, N, K, relu):
+    """nn.Linear replacement incl. head widths that are not multiples of 4 (class logits 3, angle 24, dims 3, depth 2,
+    depth bins 81): the forward writes ragged rows directly, the backward pads dy / W to 16-byte pitches."""
+    from monodetr_b200 import functional as Fn
+    _ref_setup()
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    x = torch.randn(M, K, device="cuda", generator=g, requires_grad=True)
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).requires_grad_()
+    b = torch.randn(N, device="cuda", generator=g, requires_grad=True)
+    dy = torch.randn(M, N, device="cuda", generator=g)
+    y = Fn.linear(x, w, b, relu=relu)
+    gx, gw, gb = torch.autograd.grad(y, (x, w, b), dy)
+    x2, w2, b2 = (t.detach().clone().requires_grad_() for t in (x, w, b))
+    y2 = x2 @ w2.t() + b2
+    if relu:
+        # gate with OUR activation pattern: an output within rounding error of 0 may legitimately land on either side,
+        # and one flipped gate changes a whole row of dx by O(|dy| |w|) -- a discontinuity, not an accuracy defect
+        gate = (y > 0).float()
+        assert float(((y2 > 0).float() != gate).float().mean()) < 1e-2
+        y2 = y2 * gate
+    rx, rw, rb = torch.autograd.grad(y2, (x2, w2, b2), dy)
+    assert y.shape == (M, N) and y.is_contiguous()
+    assert _report("y", y, y2) < TOL
+    assert _report("dx", gx, rx) < TOL
+    assert _report("dw", gw, rw) < TOL
+    assert _report("db", gb, rb) < TOL

@@ -118,3 +118,23 @@ def test_train_step_with_dropout_runs_and_is_finite():
             assert torch.isfinite(p.grad).all(), name
             n += 1
     assert n == 313                                                        # gradient-receiving tensors
+
+
+@pytest.mark.parametrize("B,H,W,N", [(2, 24, 80, 50), (3, 6, 20, 550), (1, 5, 7, 33)])
+def test_depth_sample_matches_grid_sample(B, H, W, N):
+    """mdb_depth_sample_* against F.grid_sample(bilinear, zeros, align_corners=True) as called at monodetr.py:248-253,
+    with centres beyond [-1, 1] to exercise the zero padding; gradient wrt the map (the centres are detached)."""
+    import torch.nn.functional as F
+    from monodetr_b200 import functional as Fn
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + N)
+    depth = torch.rand(B, H, W, device="cuda", generator=g).requires_grad_()
+    xy = torch.rand(B, N, 2, device="cuda", generator=g) * 2.4 - 1.2
+    xy[0, 0] = torch.tensor([-1.0, -1.0]); xy[0, 1] = torch.tensor([1.0, 1.0])
+    dout = torch.randn(B, N, device="cuda", generator=g)
+    out = Fn.depth_sample(depth, xy)
+    (gd,) = torch.autograd.grad(out, depth, dout)
+    d2 = depth.detach().clone().requires_grad_()
+    ref = F.grid_sample(d2[:, None], xy[:, :, None], mode="bilinear", align_corners=True).squeeze(1).squeeze(-1)
+    (rd,) = torch.autograd.grad(ref, d2, dout)
+    assert torch.allclose(out, ref, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(gd, rd, rtol=1e-5, atol=1e-5)
