@@ -36,8 +36,8 @@ constexpr int kTileABytes = BM * 128;  // 16 KiB
 constexpr int kChunkBytes = 32 * 128;  // one MN-major chunk: 32 reduction rows x 128 B
 constexpr int kThreadsTC = 192;
 constexpr int kMaxTaps = 9;
-constexpr int kPatchLd = 36;             // padded row stride (floats) of an epilogue warp's 32x32 transpose patch
-constexpr int kPatchBytes = 4 * 32 * kPatchLd * 4;   // four epilogue warps
+constexpr int kPatchBytes = 32 * 32 * 4;   // one epilogue warp's 32x32 fp32 transpose patch (XOR-swizzled 16-byte groups, no padding)
+constexpr int kEpiWarps = 4;               // epilogue warps of the 3xTF32 kernels (8 = two per TMEM lane quarter was measured slower: 128-register cap -> spills)
 
 struct TcParams {
     // ---- fprop / dgrad: decomposition of the M dimension into th x tw pixel rectangles ----------
@@ -72,7 +72,7 @@ struct TcParams {
 //                   lo = x - trunc_tf32(x) of both tiles next to the raw tiles; the MMA warp then issues
 //                   A*B + A_lo*B + A*B_lo (the tensor core truncates the raw fp32 bits itself) = ~fp32 accuracy.
 template <int BN, int STAGES, int MODE /*0 fprop/dgrad, 1 wgrad*/, bool B_MN, bool SPLIT>
-__global__ void __launch_bounds__(SPLIT ? 320 : 192)
+__global__ void __launch_bounds__(SPLIT ? 192 + 32 * kEpiWarps : 192)
 tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const __grid_constant__ TcParams p) {
     constexpr bool A_MN = (MODE == 1);
@@ -80,6 +80,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     constexpr int kRawBytes = kTileABytes + kTileBBytes;          // what TMA delivers per stage
     constexpr int kStageBytes = SPLIT ? 2 * kRawBytes : kRawBytes;  // + the lo tiles
     constexpr int kEpiWarp0 = SPLIT ? 6 : 2;                        // first epilogue warp
+    constexpr int EPI = SPLIT ? kEpiWarps : 4;                      // epilogue warps
     static_assert(!(MODE == 1) || B_MN, "wgrad reads both operands MN-major");
 
     // NOTE: index the extern array directly.  Rounding the pointer up through uintptr_t made the compiler lose the
@@ -106,11 +107,11 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         t.img = t.y0 = t.x0 = t.m0 = t.red_begin = t.tap = 0;
         if constexpr (MODE == 0) {
             const int per_img = p.tiles_x * p.tiles_y;
+            t.iters = p.ntaps * p.cblocks;
             t.img = r / per_img;
             r -= t.img * per_img;
             t.y0 = (r / p.tiles_x) * p.th;
             t.x0 = (r % p.tiles_x) * p.tw;
-            t.iters = p.ntaps * p.cblocks;
         } else {
             t.m0 = (r % p.n_tiles_m) * BM;
             r /= p.n_tiles_m;
@@ -134,7 +135,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4);                         // one arrival per epilogue warp
+            mbar_init(&tmem_empty[a], EPI);                       // one arrival per epilogue warp
         }
         fence_mbar_init();
     }
@@ -271,10 +272,11 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         // ================================ epilogue warps ===========================================
         // TMEM gives thread `lane` the accumulator ROW q*32+lane (32 consecutive columns per tcgen05.ld).  Writing
         // that straight out would touch 32 different cache lines per store instruction, so every 32x32 block is
-        // transposed through a private padded smem patch: afterwards 8 lanes x float4 cover one row's 128 bytes and
+        // transposed through a private XOR-swizzled smem patch: afterwards 8 lanes x float4 cover one row's 128 bytes and
         // a warp instruction moves 4 full lines -- residual / mask reads use the same coalesced pattern.
         const int q = warp & 3;                // TMEM lane quarter this warp may access
-        float* patch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256) + (warp - kEpiWarp0) * (32 * kPatchLd);
+        float* patch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256) + (warp - kEpiWarp0) * (32 * 32);
+        const int chunk0 = ((warp - kEpiWarp0) >> 2) * 32;       // EPI == 8: warps 4..7 take the odd 32-column chunks
         const int r4 = lane >> 3, c4 = lane & 7;
         int lt = 0;
         for (int tix = blockIdx.x; tix < p.total_tiles; tix += gridDim.x) {
@@ -309,10 +311,13 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             }
             if (dbg) p.dbg[lt * 16 + 1] = clock64();
             const uint32_t taddr_row = tmem_base + slot * BN + ((uint32_t)(q * 32) << 16);
-            const float* prow = patch + r4 * kPatchLd + c4 * 4;          // this lane's read window into the transposed patch
+            // patch element (row, 16-byte group g) lives at row * 32 + ((g ^ (row & 7)) << 2): conflict-free for the row-per-lane
+            // writes (8 lanes = 8 groups) and for the 8-lanes-per-row reads.  This lane reads rows i * 4 + r4, group c4.
+            const float* prow0 = patch + r4 * 32 + ((c4 ^ r4) << 2);            // even i
+            const float* prow1 = patch + r4 * 32 + ((c4 ^ r4 ^ 4) << 2);        // odd i
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                if (t.n0 + c0 >= p.No) break;  // uniform across the CTA
+            for (int c0 = chunk0; c0 < BN; c0 += 32 * (EPI / 4)) {
+                if (t.n0 + c0 >= p.No) break;  // uniform across the warp
                 const int n = t.n0 + c0 + c4 * 4;
                 const bool full = (t.n0 + c0 + 32 <= p.No) && !(p.ldo & 3);   // uniform: every lane's float4 is in range and 16B aligned
                 // Issue the global reads of this chunk (residual / ReLU mask / bias, read-only path) BEFORE waiting on
@@ -343,7 +348,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 if (dbg && c0 < 128) p.dbg[lt * 16 + 2 + (c0 >> 5) * 3] = clock64();
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<uint4*>(patch + lane * kPatchLd + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    *reinterpret_cast<uint4*>(patch + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                 __syncwarp();
                 if (dbg && c0 < 128) p.dbg[lt * 16 + 3 + (c0 >> 5) * 3] = clock64();
                 if (full) {
@@ -353,7 +358,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     auto rows = [&](auto RES, auto RELU, auto MASK, auto ROUND, auto ATOMIC) {
                         float4 a[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(prow + i * 4 * kPatchLd);
+                        for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(((i & 1) ? prow1 : prow0) + i * 4 * 32);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             float4 v = make_float4(fmaf(a[i].x, rsc[i], bias4.x), fmaf(a[i].y, rsc[i], bias4.y),
@@ -399,7 +404,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll 1
                         for (int e = 0; e < 4 && n + e < p.No; ++e) {
                             const size_t o = (size_t)roff[i] + n + e;
-                            float x = prow[i * 4 * kPatchLd + e] * rsc[i];
+                            float x = ((i & 1) ? prow1 : prow0)[i * 4 * 32 + e] * rsc[i];
                             if (p.bias) x += p.bias[n + e];
                             if (p.residual) x += p.residual[o];
                             if (p.relu) x = fmaxf(x, 0.f);
@@ -490,8 +495,10 @@ int num_sms_tc() {
 // launched persistent with min(total_tiles, SMs * resident CTAs) CTAs.
 template <int BN, int STAGES, int MODE, bool B_MN, bool SPLIT>
 int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, dim3 grid, cudaStream_t stream) {
-    constexpr int smem = STAGES * (SPLIT ? 2 : 1) * (kTileABytes + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/ + kPatchBytes;
-    constexpr int threads = SPLIT ? 320 : 192;
+    constexpr int smem = STAGES * (SPLIT ? 2 : 1) * (kTileABytes + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/ +
+                         (SPLIT ? kEpiWarps : 4) * kPatchBytes;
+    static_assert(smem <= 227 * 1024, "dynamic shared memory budget");
+    constexpr int threads = SPLIT ? 192 + 32 * kEpiWarps : 192;
     static bool configured = false;
     auto kern = tc_conv_gemm_kernel<BN, STAGES, MODE, B_MN, SPLIT>;
     if (!configured) {
