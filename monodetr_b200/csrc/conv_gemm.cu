@@ -71,14 +71,24 @@ struct TcParams {
 //   warps 2-5       (SPLIT only) splitter warps: error-compensated "3xTF32".  For every landed stage they write
 //                   lo = x - trunc_tf32(x) of both tiles next to the raw tiles; the MMA warp then issues
 //                   A*B + A_lo*B + A*B_lo (the tensor core truncates the raw fp32 bits itself) = ~fp32 accuracy.
-template <int BN, int STAGES, int MODE /*0 fprop/dgrad, 1 wgrad*/, bool B_MN, bool SPLIT>
+template <int BN, int STAGES, int MODE /*0 fprop/dgrad, 1 wgrad*/, bool B_MN, bool SPLIT, bool TA = false>
 __global__ void __launch_bounds__(SPLIT ? 192 + 32 * kEpiWarps : 192)
 tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const __grid_constant__ TcParams p) {
     constexpr bool A_MN = (MODE == 1);
     constexpr int kTileBBytes = BN * 128;
     constexpr int kRawBytes = kTileABytes + kTileBBytes;          // what TMA delivers per stage
-    constexpr int kStageBytes = SPLIT ? 2 * kRawBytes : kRawBytes;  // + the lo tiles
+    // TA (3xTF32, K-major A): the A tile and its lo part live in TENSOR MEMORY, not smem.  The splitter warps copy each
+    // landed A row smem -> registers -> TMEM (tcgen05.st) next to the lo part they compute, and the MMAs take A from TMEM
+    // ([a_tmem] operand form).  Per k-block that removes 3 tensor-core reads and 1 write of a 16 KB tile from the shared
+    // memory pipe -- the kernel is smem-bandwidth bound (TMA fill + splitter + 3 operand sweeps = 192 KB per k-block at
+    // 128 B/clk, profiles/r01_conv_gemm_timeline_k256.txt) -- and frees the smem for one more pipeline stage.
+    // TMEM columns: [0, 2*BN) two accumulators, then per stage 32 columns raw A + 32 columns lo A.
+    static_assert(!TA || (SPLIT && MODE == 0), "TMEM-resident A: 3xTF32 fprop/dgrad only");
+    static_assert(!TA || 2 * BN + 64 * STAGES <= 512, "TMEM budget");
+    constexpr int kStageBytes = TA ? kTileABytes + 2 * kTileBBytes : (SPLIT ? 2 * kRawBytes : kRawBytes);  // + the lo tiles
+    constexpr int kBLoOff = TA ? kTileBBytes : kRawBytes;          // B lo relative to B raw
+    constexpr int kTmemCols = TA ? 512 : 2 * BN;
     constexpr int kEpiWarp0 = SPLIT ? 6 : 2;                        // first epilogue warp
     constexpr int EPI = SPLIT ? kEpiWarps : 4;                      // epilogue warps
     static_assert(!(MODE == 1) || B_MN, "wgrad reads both operands MN-major");
@@ -139,7 +149,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
+    if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -226,12 +236,20 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         const uint32_t ao = A_MN ? k * 1024 : k * 32, bo = B_MN ? k * 1024 : k * 32;
                         const uint64_t adesc = kDescHiA | (uint64_t)(kDescLoA | (((a_addr + ao) >> 4) & 0x3FFFu));
                         const uint64_t bdesc = kDescHiB | (uint64_t)(kDescLoB | (((b_addr + bo) >> 4) & 0x3FFFu));
-                        umma_tf32(tacc, adesc, bdesc, idesc, (it > 0) || (k > 0));
-                        if constexpr (SPLIT) {
-                            const uint64_t alo = kDescHiA | (uint64_t)(kDescLoA | (((a_addr + kRawBytes + ao) >> 4) & 0x3FFFu));
-                            const uint64_t blo = kDescHiB | (uint64_t)(kDescLoB | (((b_addr + kRawBytes + bo) >> 4) & 0x3FFFu));
-                            umma_tf32(tacc, alo, bdesc, idesc, true);
-                            umma_tf32(tacc, adesc, blo, idesc, true);
+                        if constexpr (TA) {
+                            const uint32_t ta = tmem_base + 2 * BN + s * 64 + k * 8;      // raw A columns of this k-step; lo at +32
+                            const uint64_t blo = kDescHiB | (uint64_t)(kDescLoB | (((b_addr + kBLoOff + bo) >> 4) & 0x3FFFu));
+                            umma_tf32_ta(tacc, ta, bdesc, idesc, (it > 0) || (k > 0));
+                            umma_tf32_ta(tacc, ta + 32, bdesc, idesc, true);
+                            umma_tf32_ta(tacc, ta, blo, idesc, true);
+                        } else {
+                            umma_tf32(tacc, adesc, bdesc, idesc, (it > 0) || (k > 0));
+                            if constexpr (SPLIT) {
+                                const uint64_t alo = kDescHiA | (uint64_t)(kDescLoA | (((a_addr + kRawBytes + ao) >> 4) & 0x3FFFu));
+                                const uint64_t blo = kDescHiB | (uint64_t)(kDescLoB | (((b_addr + kRawBytes + bo) >> 4) & 0x3FFFu));
+                                umma_tf32(tacc, alo, bdesc, idesc, true);
+                                umma_tf32(tacc, adesc, blo, idesc, true);
+                            }
                         }
                     }
                     umma_commit(&empty_bar[s]);                   // frees the smem stage when these MMAs retire
@@ -251,17 +269,51 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 const int s = git % STAGES;
                 const uint32_t ph = (git / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
-                const uint4* raw = reinterpret_cast<const uint4*>(smem + s * kStageBytes);
-                float4* lo = reinterpret_cast<float4*>(smem + s * kStageBytes + kRawBytes);
+                if constexpr (TA) {
+                    // A: this thread owns tile row (warp % 4) * 32 + lane = its TMEM lane.  K-major SWIZZLE_128B smem: row r
+                    // is 128 bytes, 16-byte chunk c sits at c ^ (r & 7) (conflict-free: 8 lanes hit 8 different chunks).
+                    const int row = (warp & 3) * 32 + lane;
+                    const uint8_t* arow = smem + s * kStageBytes + row * 128;
+                    uint32_t hi[32], lo32[32];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 r = *reinterpret_cast<const uint4*>(arow + ((c ^ (row & 7)) << 4));
+                        hi[4 * c] = r.x; hi[4 * c + 1] = r.y; hi[4 * c + 2] = r.z; hi[4 * c + 3] = r.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        lo32[j] = __float_as_uint(__uint_as_float(hi[j]) - __uint_as_float(hi[j] & 0xFFFFE000u));
+                    const uint32_t ta = tmem_base + 2 * BN + s * 64 + ((uint32_t)((warp & 3) * 32) << 16);
+                    tmem_st_32x32(ta, hi);
+                    tmem_st_32x32(ta + 32, lo32);
+                    // B: lo part elementwise, as in the smem-only variant
+                    const uint4* raw = reinterpret_cast<const uint4*>(smem + s * kStageBytes + kTileABytes);
+                    float4* lo = reinterpret_cast<float4*>(smem + s * kStageBytes + kTileABytes + kTileBBytes);
 #pragma unroll 4
-                for (int i = tid; i < kRawBytes / 16; i += 128) {
-                    const uint4 r = raw[i];
-                    float4 l;
-                    l.x = __uint_as_float(r.x) - __uint_as_float(r.x & 0xFFFFE000u);
-                    l.y = __uint_as_float(r.y) - __uint_as_float(r.y & 0xFFFFE000u);
-                    l.z = __uint_as_float(r.z) - __uint_as_float(r.z & 0xFFFFE000u);
-                    l.w = __uint_as_float(r.w) - __uint_as_float(r.w & 0xFFFFE000u);
-                    lo[i] = l;
+                    for (int i = tid; i < kTileBBytes / 16; i += 128) {
+                        const uint4 r = raw[i];
+                        float4 l;
+                        l.x = __uint_as_float(r.x) - __uint_as_float(r.x & 0xFFFFE000u);
+                        l.y = __uint_as_float(r.y) - __uint_as_float(r.y & 0xFFFFE000u);
+                        l.z = __uint_as_float(r.z) - __uint_as_float(r.z & 0xFFFFE000u);
+                        l.w = __uint_as_float(r.w) - __uint_as_float(r.w & 0xFFFFE000u);
+                        lo[i] = l;
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();             // order the TMEM stores before the MMA thread's reads (pairs with its fence::after)
+                } else {
+                    const uint4* raw = reinterpret_cast<const uint4*>(smem + s * kStageBytes);
+                    float4* lo = reinterpret_cast<float4*>(smem + s * kStageBytes + kRawBytes);
+#pragma unroll 4
+                    for (int i = tid; i < kRawBytes / 16; i += 128) {
+                        const uint4 r = raw[i];
+                        float4 l;
+                        l.x = __uint_as_float(r.x) - __uint_as_float(r.x & 0xFFFFE000u);
+                        l.y = __uint_as_float(r.y) - __uint_as_float(r.y & 0xFFFFE000u);
+                        l.z = __uint_as_float(r.z) - __uint_as_float(r.z & 0xFFFFE000u);
+                        l.w = __uint_as_float(r.w) - __uint_as_float(r.w & 0xFFFFE000u);
+                        lo[i] = l;
+                    }
                 }
                 fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 __syncwarp();
@@ -430,7 +482,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<2 * BN>(tmem_base);
+        tmem_dealloc<kTmemCols>(tmem_base);
     }
 }
 
@@ -493,14 +545,14 @@ int num_sms_tc() {
 
 // `grid` carries the logical tile counts (x = column tiles, y = row tiles, z = split-K slices); the kernel is
 // launched persistent with min(total_tiles, SMs * resident CTAs) CTAs.
-template <int BN, int STAGES, int MODE, bool B_MN, bool SPLIT>
+template <int BN, int STAGES, int MODE, bool B_MN, bool SPLIT, bool TA = false>
 int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, dim3 grid, cudaStream_t stream) {
-    constexpr int smem = STAGES * (SPLIT ? 2 : 1) * (kTileABytes + BN * 128) + 1024 /*align slack*/ + 256 /*barriers*/ +
-                         (SPLIT ? kEpiWarps : 4) * kPatchBytes;
+    constexpr int stage = TA ? kTileABytes + 2 * BN * 128 : (SPLIT ? 2 : 1) * (kTileABytes + BN * 128);
+    constexpr int smem = STAGES * stage + 1024 /*align slack*/ + 256 /*barriers*/ + (SPLIT ? kEpiWarps : 4) * kPatchBytes;
     static_assert(smem <= 227 * 1024, "dynamic shared memory budget");
     constexpr int threads = SPLIT ? 192 + 32 * kEpiWarps : 192;
     static bool configured = false;
-    auto kern = tc_conv_gemm_kernel<BN, STAGES, MODE, B_MN, SPLIT>;
+    auto kern = tc_conv_gemm_kernel<BN, STAGES, MODE, B_MN, SPLIT, TA>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
@@ -509,7 +561,7 @@ int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, dim3 grid,
     p.n_tiles_n = (int)grid.x;
     p.n_tiles_m = (int)grid.y;
     p.total_tiles = (int)(grid.x * grid.y * grid.z);
-    const int resident = (smem <= 112 * 1024 && 2 * BN * 2 <= 512) ? 2 : 1;   // smem and TMEM (2*BN columns per CTA)
+    const int resident = (!TA && smem <= 112 * 1024 && 2 * BN * 2 <= 512) ? 2 : 1;   // smem and TMEM (2*BN columns per CTA, 512 with TA)
     int ctas = num_sms_tc() * resident;
     if (ctas > p.total_tiles) ctas = p.total_tiles;
     if (ctas < 1) return 0;
@@ -608,10 +660,13 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
         if (rc) return rc;
     }
     dim3 grid((Cout + bn - 1) / bn, B * p.tiles_x * p.tiles_y, 1);
-    if (bn == 64) return (g_precision == 1) ? launch_tc<64, 4, 0, false, true>(ma, mb, p, grid, stream)
+    static const bool tmem_a = getenv("MDB_NO_TMEM_A") == nullptr;            // A/B switch (profiling)
+    if (bn == 64) return (g_precision == 1) ? (tmem_a ? launch_tc<64, 6, 0, false, true, true>(ma, mb, p, grid, stream)
+                                                      : launch_tc<64, 4, 0, false, true>(ma, mb, p, grid, stream))
                                             : launch_tc<64, 6, 0, false, false>(ma, mb, p, grid, stream);
     if (g_precision == 1 && wide) return launch_tc<256, 2, 0, false, true>(ma, mb, p, grid, stream);
-    if (g_precision == 1) return launch_tc<128, 3, 0, false, true>(ma, mb, p, grid, stream);
+    if (g_precision == 1) return tmem_a ? launch_tc<128, 4, 0, false, true, true>(ma, mb, p, grid, stream)
+                                        : launch_tc<128, 3, 0, false, true>(ma, mb, p, grid, stream);
     if (wide) return launch_tc<256, 4, 0, false, false>(ma, mb, p, grid, stream);
     return launch_tc<128, 5, 0, false, false>(ma, mb, p, grid, stream);
 }
@@ -676,7 +731,9 @@ int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* re
             if (nt == 0) {   // no tap reaches this parity class (1x1 stride 2): result = (0 + residual) * mask
                 p.ntaps = 0;
             }
-            rc = (g_precision == 1) ? launch_tc<128, 3, 0, true, true>(ma, mb, p, grid, stream)
+            static const bool tmem_a = getenv("MDB_NO_TMEM_A") == nullptr;
+            rc = (g_precision == 1) ? (tmem_a ? launch_tc<128, 4, 0, true, true, true>(ma, mb, p, grid, stream)
+                                              : launch_tc<128, 3, 0, true, true>(ma, mb, p, grid, stream))
                                     : launch_tc<128, 5, 0, true, false>(ma, mb, p, grid, stream);
             if (rc) return rc;
         }
