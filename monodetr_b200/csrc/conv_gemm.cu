@@ -84,7 +84,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // memory pipe -- the kernel is smem-bandwidth bound (TMA fill + splitter + 3 operand sweeps = 192 KB per k-block at
     // 128 B/clk, profiles/r01_conv_gemm_timeline_k256.txt) -- and frees the smem for one more pipeline stage.
     // TMEM columns: [0, 2*BN) two accumulators, then per stage 32 columns raw A + 32 columns lo A.
-    static_assert(!TA || (SPLIT && MODE == 0), "TMEM-resident A: 3xTF32 fprop/dgrad only");
+    static_assert(!TA || SPLIT, "TMEM-resident A: 3xTF32 kernels only");
     static_assert(!TA || 2 * BN + 64 * STAGES <= 512, "TMEM budget");
     constexpr int kStageBytes = TA ? kTileABytes + 2 * kTileBBytes : (SPLIT ? 2 * kRawBytes : kRawBytes);  // + the lo tiles
     constexpr int kBLoOff = TA ? kTileBBytes : kRawBytes;          // B lo relative to B raw
@@ -202,7 +202,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     } else if (warp == 1) {
         // ================================ MMA issuer ==============================================
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_tf32(BM, BN, A_MN, B_MN);
+            constexpr uint32_t idesc = make_idesc_tf32(BM, BN, A_MN && !TA, B_MN);   // A from TMEM is always lane = m, column = k
             constexpr uint64_t kDescHiA = (A_MN ? make_smem_desc(0, kChunkBytes, 512, 1) : make_smem_desc(0, 16, 1024, 2)) & 0xFFFFFFFF00000000ull;
             constexpr uint64_t kDescHiB = (B_MN ? make_smem_desc(0, kChunkBytes, 512, 1) : make_smem_desc(0, 16, 1024, 2)) & 0xFFFFFFFF00000000ull;
             constexpr uint32_t kDescLoA = (uint32_t)((A_MN ? make_smem_desc(0, kChunkBytes, 512, 1) : make_smem_desc(0, 16, 1024, 2)) & 0xFFFF0000ull);
@@ -273,12 +273,23 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     // A: this thread owns tile row (warp % 4) * 32 + lane = its TMEM lane.  K-major SWIZZLE_128B smem: row r
                     // is 128 bytes, 16-byte chunk c sits at c ^ (r & 7) (conflict-free: 8 lanes hit 8 different chunks).
                     const int row = (warp & 3) * 32 + lane;
-                    const uint8_t* arow = smem + s * kStageBytes + row * 128;
                     uint32_t hi[32], lo32[32];
+                    if constexpr (!A_MN) {
+                        const uint8_t* arow = smem + s * kStageBytes + row * 128;
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const uint4 r = *reinterpret_cast<const uint4*>(arow + ((c ^ (row & 7)) << 4));
-                        hi[4 * c] = r.x; hi[4 * c + 1] = r.y; hi[4 * c + 2] = r.z; hi[4 * c + 3] = r.w;
+                        for (int c = 0; c < 8; ++c) {
+                            const uint4 r = *reinterpret_cast<const uint4*>(arow + ((c ^ (row & 7)) << 4));
+                            hi[4 * c] = r.x; hi[4 * c + 1] = r.y; hi[4 * c + 2] = r.z; hi[4 * c + 3] = r.w;
+                        }
+                    } else {
+                        // wgrad: A arrives MN-major -- chunk (warp & 3) holds this warp's 32 m-columns as [32 reduction rows]
+                        // [128 B], 32-byte atoms XOR-swizzled with the row (SWIZZLE_128B_ATOM_32B: atom ^= row & 3).  A warp-wide
+                        // LDS.32 reads one full 128-byte row (conflict-free); 32 of them transpose the tile into TMEM order.
+                        const uint8_t* acol = smem + s * kStageBytes + (warp & 3) * kChunkBytes + (lane & 7) * 4;
+                        const int atom = lane >> 3;
+#pragma unroll
+                        for (int k = 0; k < 32; ++k)
+                            hi[k] = *reinterpret_cast<const uint32_t*>(acol + k * 128 + ((atom ^ (k & 3)) << 5));
                     }
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
@@ -646,7 +657,8 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
         rc = make_map(&ma, x, 4, dims, str, box, es);
         if (rc) return rc;
     }
-    static const bool wide_split = getenv("MDB_NO_WIDE_SPLIT") == nullptr;   // A/B switch (profiling)
+    // 128x256 3xTF32 tiles are only used when the TMEM-A variant is switched off (it is faster than them everywhere measured)
+    static const bool wide_split = getenv("MDB_NO_TMEM_A") != nullptr && getenv("MDB_NO_WIDE_SPLIT") == nullptr;
     // 3xTF32: a 128x256 tile needs 96 KB per stage -> only 2 stages fit, which cannot hide DRAM latency; it pays off
     // only when the A operand is re-read from L2 (multi-tap convolutions), measured +6 % on 3x3 256->256.
     const bool wide = (g_precision == 0 || (wide_split && kh * kw > 1)) && (Cout % 256 == 0) &&
@@ -794,7 +806,9 @@ int mdb_conv2d_wgrad_f32(const float* dy, const float* x, const float* rowscale,
         if (rc) return rc;
     }
     dim3 grid((Cin + bn - 1) / bn, (Cout + BM - 1) / BM, taps * splits);
-    rc = (g_precision == 1) ? launch_tc<128, 3, 1, true, true>(ma, mb, p, grid, stream)
+    static const bool tmem_a = getenv("MDB_NO_TMEM_A") == nullptr;
+    rc = (g_precision == 1) ? (tmem_a ? launch_tc<128, 4, 1, true, true, true>(ma, mb, p, grid, stream)
+                                      : launch_tc<128, 3, 1, true, true>(ma, mb, p, grid, stream))
          : (bn == 256)      ? launch_tc<256, 4, 1, true, false>(ma, mb, p, grid, stream)
                             : launch_tc<128, 5, 1, true, false>(ma, mb, p, grid, stream);
     if (rc) return rc;
