@@ -224,7 +224,7 @@ def run_msda_b200(args, rank, local_rank, ws):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "msda_fwd_vec_kernel<8>", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"],
+        "roofline": {"kernel": "msda_fwd_d32_kernel", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
                      "algorithmic_bytes": fwd_bytes, "avg_ms": fwd_ms},
         "roofline_bwd": {"kernel": "msda_bwd_vec_kernel<8,4>(+memset)", "bound": "hbm",

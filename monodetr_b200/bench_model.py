@@ -203,10 +203,10 @@ def run(args, rank, local_rank, ws):
     }
     if enc_ms:
         ach = fwd_bytes / (enc_ms * 1e-3) / 1e9
-        line["roofline"] = {"kernel": "msda_fwd_vec_kernel<8> (encoder call, Lq=10200, in situ)", "bound": "hbm", "achieved": ach,
+        line["roofline"] = {"kernel": "msda_fwd_d32_kernel (encoder call, Lq=10200, in situ)", "bound": "hbm", "achieved": ach,
                             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                             # dram__bytes_read.sum + dram__bytes_write.sum of this launch at B=8 from the committed capture
-                            # profiles/r01_msda_model_r1.txt (239.7 MB + 70.8 MB); scaled with the batch
-                            "traffic": int(310.47e6 * B / 8),
+                            # profiles/r01_msda_fwd_d32_model.txt (239.9 MB + 72.1 MB); scaled with the batch
+                            "traffic": int(311.97e6 * B / 8),
                             "peak_source": pk["source"], "algorithmic_bytes": fwd_bytes, "avg_ms": enc_ms}
     return line

@@ -150,13 +150,15 @@ __global__ void round_tf32_kernel(const float* __restrict__ x, float* __restrict
 }
 
 // ---- stem: y[b][oy][ox][64] = relu(scale[c] * conv7x7s2(x NCHW [b][3][H][W]) + bias[c]) ----------------
-// CTA = 8 x 32 output pixels, 256 threads, one pixel per thread, 64 accumulators per thread.
+// CTA = 8 x 32 output pixels, 256 threads.  A thread owns TWO vertically adjacent pixels x 32 of the 64 channels
+// (warp w: rows 2*(w>>1), +1; channel half w&1): a tap's 8 weight float4 (warp-broadcast LDS.128) feed 64 FMAs, so the
+// loop is FMA-bound instead of LDS-bound (the one-pixel-per-thread version needed 16 weight loads per 64 FMAs).
 constexpr int ST_TH = 8, ST_TW = 32, ST_C = 64, ST_K = 7;
 constexpr int ST_IH = ST_TH * 2 + 5, ST_IW = ST_TW * 2 + 5;   // 21 x 69 input patch per channel
 
 __global__ void __launch_bounds__(256)
 stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][3][7][7]*/, const float* __restrict__ scale,
-                 const float* __restrict__ bias, float* __restrict__ y, int H, int W, int Ho, int Wo) {
+                 const float* __restrict__ bias, float* __restrict__ y, int H, int W, int Ho, int Wo, int round_out) {
     extern __shared__ float sm[];
     float* s_w = sm;                          // [147][64]  (tap-major so a tap's 64 weights are contiguous)
     float* s_in = sm + 147 * ST_C;            // [3][21][69]
@@ -174,41 +176,49 @@ stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64]
         s_in[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? x[(((size_t)b * 3 + ch) * H + gy) * W + gx] : 0.f;
     }
     __syncthreads();
-    const int ly = threadIdx.x / ST_TW, lx = threadIdx.x % ST_TW;
-    float acc[ST_C];
+    const int wrp = threadIdx.x >> 5, lx = threadIdx.x & 31;
+    const int half = wrp & 1, ly = (wrp >> 1) * 2;            // pixels (ly, lx) and (ly + 1, lx)
+    float acc0[ST_C / 2], acc1[ST_C / 2];
 #pragma unroll
-    for (int c = 0; c < ST_C; ++c) acc[c] = 0.f;
+    for (int c = 0; c < ST_C / 2; ++c) acc0[c] = acc1[c] = 0.f;
     for (int ch = 0; ch < 3; ++ch)
         for (int ky = 0; ky < ST_K; ++ky) {
-            const float* row = s_in + (ch * ST_IH + ly * 2 + ky) * ST_IW + lx * 2;
+            const float* row0 = s_in + (ch * ST_IH + ly * 2 + ky) * ST_IW + lx * 2;
+            const float* row1 = row0 + 2 * ST_IW;
 #pragma unroll
             for (int kx = 0; kx < ST_K; ++kx) {
-                const float v = row[kx];
-                const float4* wp = reinterpret_cast<const float4*>(s_w + ((ch * ST_K + ky) * ST_K + kx) * ST_C);
+                const float v0 = row0[kx], v1 = row1[kx];
+                const float4* wp = reinterpret_cast<const float4*>(s_w + ((ch * ST_K + ky) * ST_K + kx) * ST_C + half * (ST_C / 2));
 #pragma unroll
-                for (int c4 = 0; c4 < ST_C / 4; ++c4) {
+                for (int c4 = 0; c4 < ST_C / 8; ++c4) {
                     const float4 ww = wp[c4];
-                    acc[c4 * 4] = fmaf(v, ww.x, acc[c4 * 4]);
-                    acc[c4 * 4 + 1] = fmaf(v, ww.y, acc[c4 * 4 + 1]);
-                    acc[c4 * 4 + 2] = fmaf(v, ww.z, acc[c4 * 4 + 2]);
-                    acc[c4 * 4 + 3] = fmaf(v, ww.w, acc[c4 * 4 + 3]);
+                    acc0[c4 * 4] = fmaf(v0, ww.x, acc0[c4 * 4]);         acc1[c4 * 4] = fmaf(v1, ww.x, acc1[c4 * 4]);
+                    acc0[c4 * 4 + 1] = fmaf(v0, ww.y, acc0[c4 * 4 + 1]); acc1[c4 * 4 + 1] = fmaf(v1, ww.y, acc1[c4 * 4 + 1]);
+                    acc0[c4 * 4 + 2] = fmaf(v0, ww.z, acc0[c4 * 4 + 2]); acc1[c4 * 4 + 2] = fmaf(v1, ww.z, acc1[c4 * 4 + 2]);
+                    acc0[c4 * 4 + 3] = fmaf(v0, ww.w, acc0[c4 * 4 + 3]); acc1[c4 * 4 + 3] = fmaf(v1, ww.w, acc1[c4 * 4 + 3]);
                 }
             }
         }
-    const int oy = oy0 + ly, ox = ox0 + lx;
-    if (oy < Ho && ox < Wo) {
-        float* yp = y + (((size_t)b * Ho + oy) * Wo + ox) * ST_C;
+    const int ox = ox0 + lx;
+    if (ox < Wo) {
 #pragma unroll
-        for (int c4 = 0; c4 < ST_C / 4; ++c4) {
-            const float4 s = *reinterpret_cast<const float4*>(scale + c4 * 4);
-            const float4 bb = *reinterpret_cast<const float4*>(bias + c4 * 4);
-            float4 o;
-            o.x = fmaxf(fmaf(acc[c4 * 4], s.x, bb.x), 0.f);
-            o.y = fmaxf(fmaf(acc[c4 * 4 + 1], s.y, bb.y), 0.f);
-            o.z = fmaxf(fmaf(acc[c4 * 4 + 2], s.z, bb.z), 0.f);
-            o.w = fmaxf(fmaf(acc[c4 * 4 + 3], s.w, bb.w), 0.f);
-            o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w);
-            *reinterpret_cast<float4*>(yp + c4 * 4) = o;
+        for (int pxl = 0; pxl < 2; ++pxl) {
+            const int oy = oy0 + ly + pxl;
+            if (oy >= Ho) break;
+            float* yp = y + (((size_t)b * Ho + oy) * Wo + ox) * ST_C + half * (ST_C / 2);
+#pragma unroll
+            for (int c4 = 0; c4 < ST_C / 8; ++c4) {
+                const float4 s = *reinterpret_cast<const float4*>(scale + half * (ST_C / 2) + c4 * 4);
+                const float4 bb = *reinterpret_cast<const float4*>(bias + half * (ST_C / 2) + c4 * 4);
+                const float* a = pxl ? acc1 : acc0;
+                float4 o;
+                o.x = fmaxf(fmaf(a[c4 * 4], s.x, bb.x), 0.f);
+                o.y = fmaxf(fmaf(a[c4 * 4 + 1], s.y, bb.y), 0.f);
+                o.z = fmaxf(fmaf(a[c4 * 4 + 2], s.z, bb.z), 0.f);
+                o.w = fmaxf(fmaf(a[c4 * 4 + 3], s.w, bb.w), 0.f);
+                if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+                *reinterpret_cast<float4*>(yp + c4 * 4) = o;
+            }
         }
     }
 }
@@ -292,7 +302,8 @@ int mdb_stem_conv7x7_bn_relu_f32(const float* x, const float* w, const float* sc
         configured = true;
     }
     dim3 grid((Wo + ST_TW - 1) / ST_TW, (Ho + ST_TH - 1) / ST_TH, B);
-    stem_conv_kernel<<<grid, 256, smem, stream>>>(x, w, scale, bias, y, H, W, Ho, Wo);
+    // single-pass TF32 mode: the consumer is a tensor-core operand that expects round-to-nearest TF32 values
+    stem_conv_kernel<<<grid, 256, smem, stream>>>(x, w, scale, bias, y, H, W, Ho, Wo, mdb_get_precision() == 0 ? 1 : 0);
     return (int)cudaGetLastError();
 }
 
