@@ -96,6 +96,11 @@ int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* re
 int mdb_conv2d_wgrad_f32(const float* dy, const float* x, const float* rowscale /*[Cout]|NULL*/, float* dw_packed,
                          int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
                          int accumulate, void* stream);
+/* Same, plus db[Cout] (+)= sum over output pixels of dy: the bias gradient of nn.Conv2d / nn.Linear, produced by the
+ * same launch (zero-filled first unless accumulate; db may sit directly behind dw_packed to share the memset). */
+int mdb_conv2d_wgrad_bias_f32(const float* dy, const float* x, const float* rowscale /*[Cout]|NULL*/, float* dw_packed,
+                              float* db /*[Cout]|NULL*/, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride,
+                              int pad, int accumulate, void* stream);
 /* w_packed[t][o][i] = w_oihw[o][i][t] * (scale ? scale[o] : 1), rounded to nearest TF32 in precision mode 0
  * (FrozenBatchNorm fold, backbone.py:54-64) */
 int mdb_pack_conv_weight_f32(const float* w_oihw, const float* scale, float* w_packed, int O, int I, int taps,

@@ -27,6 +27,7 @@ SIGNATURES = {
     "mdb_conv2d_forward_f32": [_PTR] * 5 + [c_int] * 10 + [_PTR],
     "mdb_conv2d_dgrad_f32": [_PTR] * 5 + [c_int] * 10 + [_PTR],
     "mdb_conv2d_wgrad_f32": [_PTR] * 4 + [c_int] * 10 + [_PTR],
+    "mdb_conv2d_wgrad_bias_f32": [_PTR] * 5 + [c_int] * 10 + [_PTR],
     "mdb_pack_conv_weight_f32": [_PTR] * 3 + [c_int] * 3 + [_PTR],
     "mdb_unpack_conv_wgrad_f32": [_PTR] * 2 + [c_int] * 4 + [_PTR],
     "mdb_colsum_f32": [_PTR] * 2 + [ctypes.c_longlong, c_int, c_int, _PTR],

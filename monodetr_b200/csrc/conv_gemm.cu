@@ -59,6 +59,7 @@ struct TcParams {
     const float* residual;           // same indexing as out, or null
     const float* relu_mask;          // same indexing as out: out *= (mask > 0), or null
     const float* rowscale;           // wgrad: [Mo_rows] or null
+    float* colsum_out;               // wgrad (TMEM-A kernels): [Mo_rows] += column sums of dy (bias gradient), or null
     float* out;
     long long* dbg;                  // profiling aid (tools/diag_timeline.py): clock64 stamps of CTA 0, or null
 };
@@ -265,6 +266,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         int git = 0;
         for (int tix = blockIdx.x; tix < p.total_tiles; tix += gridDim.x) {
             const Tile t = decode(tix);
+            [[maybe_unused]] float rsum = 0.f;                    // wgrad bias gradient: this thread's dy channel summed over pixels
             for (int it = 0; it < t.iters; ++it, ++git) {
                 const int s = git % STAGES;
                 const uint32_t ph = (git / STAGES) & 1;
@@ -290,6 +292,15 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
                         for (int k = 0; k < 32; ++k)
                             hi[k] = *reinterpret_cast<const uint32_t*>(acol + k * 128 + ((atom ^ (k & 3)) << 5));
+                        // Bias gradient for free: thread = one dy channel, the 32 values = 32 pixels of the reduction tile
+                        // (TMA zero-fills pixels / channels past the edge).  Four partial sums keep the add chain short.
+                        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 32; k += 4) {
+                            q0 += __uint_as_float(hi[k]); q1 += __uint_as_float(hi[k + 1]);
+                            q2 += __uint_as_float(hi[k + 2]); q3 += __uint_as_float(hi[k + 3]);
+                        }
+                        rsum += (q0 + q1) + (q2 + q3);
                     }
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
@@ -329,6 +340,11 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&split_bar[s]);
+            }
+            if constexpr (TA && A_MN) {
+                // every (column tile, tap) re-reads the same dy tiles: only column tile 0 / tap 0 contributes
+                const int m = t.m0 + (warp & 3) * 32 + lane;
+                if (p.colsum_out && t.n0 == 0 && t.tap == 0 && t.iters > 0 && m < p.Mo_rows) atomicAdd(p.colsum_out + m, rsum);
             }
         }
     } else if (warp >= kEpiWarp0) {
@@ -756,18 +772,36 @@ int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* re
 // dw_packed is zero-filled by the call unless accumulate != 0.
 int mdb_conv2d_wgrad_f32(const float* dy, const float* x, const float* rowscale, float* dw_packed, int B, int H, int W,
                          int Cin, int Cout, int kh, int kw, int stride, int pad, int accumulate, void* stream_) {
+    return mdb_conv2d_wgrad_bias_f32(dy, x, rowscale, dw_packed, nullptr, B, H, W, Cin, Cout, kh, kw, stride, pad, accumulate, stream_);
+}
+
+// Same, plus db[Cout] (+)= sum over pixels of dy (the bias gradient) -- a by-product of the 3xTF32 kernel's operand
+// staging (the splitter thread that moves dy channel m into tensor memory sums it on the way); the single-pass TF32
+// mode has no splitter and runs the stand-alone column-sum kernel instead.
+int mdb_conv2d_wgrad_bias_f32(const float* dy, const float* x, const float* rowscale, float* dw_packed, float* db, int B, int H,
+                              int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int accumulate, void* stream_) {
     ConvGeom g{B, H, W, Cin, Cout, kh, kw, stride, pad, (H + 2 * pad - kh) / stride + 1, (W + 2 * pad - kw) / stride + 1};
     int rc = check_geom(g);
     if (rc) return rc;
     if (!dy || !x || !dw_packed) return MDB_EINVAL;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int taps = kh * kw;
+    static const bool tmem_a = getenv("MDB_NO_TMEM_A") == nullptr;
+    const bool fused_db = db && g_precision == 1 && tmem_a;
     if (!accumulate) {
-        cudaError_t e = cudaMemsetAsync(dw_packed, 0, sizeof(float) * (size_t)taps * Cout * Cin, stream);
+        // db directly behind dw_packed (as monodetr_b200.tc allocates them): one memset node instead of two
+        const bool adjacent = fused_db && db == dw_packed + (size_t)taps * Cout * Cin;
+        cudaError_t e = cudaMemsetAsync(dw_packed, 0, sizeof(float) * ((size_t)taps * Cout * Cin + (adjacent ? Cout : 0)), stream);
+        if (e == cudaSuccess && fused_db && !adjacent) e = cudaMemsetAsync(db, 0, sizeof(float) * Cout, stream);
         if (e != cudaSuccess) return (int)e;
+    }
+    if (db && !fused_db) {
+        rc = mdb_colsum_f32(dy, db, (long long)B * g.Ho * g.Wo, Cout, accumulate, stream_);
+        if (rc) return rc;
     }
     TcParams p;
     memset(&p, 0, sizeof(p));
+    p.colsum_out = fused_db ? db : nullptr;
     pick_tile(g.Wo, g.Ho, 32, &p.rtw, &p.rth);
     p.rtiles_x = (g.Wo + p.rtw - 1) / p.rtw;
     p.rtiles_y = (g.Ho + p.rth - 1) / p.rth;
@@ -806,7 +840,6 @@ int mdb_conv2d_wgrad_f32(const float* dy, const float* x, const float* rowscale,
         if (rc) return rc;
     }
     dim3 grid((Cin + bn - 1) / bn, (Cout + BM - 1) / BM, taps * splits);
-    static const bool tmem_a = getenv("MDB_NO_TMEM_A") == nullptr;
     rc = (g_precision == 1) ? (tmem_a ? launch_tc<128, 4, 1, true, true, true>(ma, mb, p, grid, stream)
                                       : launch_tc<128, 3, 1, true, true>(ma, mb, p, grid, stream))
          : (bn == 256)      ? launch_tc<256, 4, 1, true, false>(ma, mb, p, grid, stream)

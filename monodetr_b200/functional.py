@@ -98,14 +98,18 @@ class _Linear(Function):
         dx = dw = db = dres = None
         if ctx.needs_input_grad[0]:
             dx = tc.linear_dgrad(dy2, wr).view(xshape)
+        want_db = has_b and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
-            dw = tc.linear_wgrad(dy2, x2)
+            if want_db:                       # bias gradient = by-product of the weight-gradient launch
+                dw, db = tc.linear_wgrad(dy2, x2, with_bias_grad=True)
+            else:
+                dw = tc.linear_wgrad(dy2, x2)
             if Np != N:
                 dw = dw[:N]
-        if has_b and ctx.needs_input_grad[2]:
+        elif want_db:
             db = tc.colsum(dy2)
-            if Np != N:
-                db = db[:N]
+        if db is not None and Np != N:
+            db = db[:N]
         if has_res and ctx.needs_input_grad[3]:
             dres = dres_src.view(*xshape[:-1], N)
         return dx, dw, db, dres, None
@@ -142,14 +146,19 @@ class _Conv2d(Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = tc.conv2d_dgrad(dy, wp, x.shape, None, None, kh, kw, stride, pad)
+        want_db = has_b and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
-            dw = tc.unpack_wgrad(tc.conv2d_wgrad(dy, x, None, kh, kw, stride, pad), kh, kw)
+            if want_db:
+                dwp, db = tc.conv2d_wgrad(dy, x, None, kh, kw, stride, pad, with_bias_grad=True)
+            else:
+                dwp = tc.conv2d_wgrad(dy, x, None, kh, kw, stride, pad)
+            dw = tc.unpack_wgrad(dwp, kh, kw)
             if Op != O:
                 dw = dw[:O]
-        if has_b and ctx.needs_input_grad[2]:
+        elif want_db:
             db = tc.colsum(dy.view(-1, Op))
-            if Op != O:
-                db = db[:O]
+        if db is not None and Op != O:
+            db = db[:O]
         return dx, dw, db, None, None
 
 

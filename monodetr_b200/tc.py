@@ -86,16 +86,21 @@ def conv2d_dgrad(dy, w_packed, x_shape, residual=None, relu_mask=None, kh=1, kw=
     return dx
 
 
-def conv2d_wgrad(dy, x, rowscale=None, kh=1, kw=1, stride=1, pad=0):
+def conv2d_wgrad(dy, x, rowscale=None, kh=1, kw=1, stride=1, pad=0, with_bias_grad=False):
+    """dw_packed (taps, Cout, Cin); with_bias_grad=True also returns db (Cout,) = dy summed over pixels, produced by the
+    same launch (both live in one allocation so a single memset zero-fills them)."""
     _chk(dy, x, rowscale)
     B, H, W, Cin = x.shape
     Cout = dy.shape[-1]
-    dwp = torch.empty((kh * kw, Cout, Cin), dtype=torch.float32, device=x.device)
-    rc = _lib.lib().mdb_conv2d_wgrad_f32(_p(dy), _p(x), _p(rowscale), _p(dwp), B, H, W, Cin, Cout, kh, kw, stride, pad, 0,
-                                         _s())
+    n = kh * kw * Cout * Cin
+    buf = torch.empty((n + (Cout if with_bias_grad else 0),), dtype=torch.float32, device=x.device)
+    dwp = buf[:n].view(kh * kw, Cout, Cin)
+    db = buf[n:] if with_bias_grad else None
+    rc = _lib.lib().mdb_conv2d_wgrad_bias_f32(_p(dy), _p(x), _p(rowscale), _p(dwp), _p(db), B, H, W, Cin, Cout, kh, kw, stride,
+                                              pad, 0, _s())
     _lib.check(rc, "conv2d_wgrad")
-    _lib.count(1)
-    return dwp
+    _lib.count(1 if (not with_bias_grad or get_precision() == "tf32x3") else 2)
+    return (dwp, db) if with_bias_grad else dwp
 
 
 # ---- linear layers = 1x1 convolution over a 1-row "image" of M pixels ---------------------------------
@@ -137,7 +142,10 @@ def linear_dgrad(dy2d, w, residual=None, relu_mask=None):
     return dx.view(M, K)
 
 
-def linear_wgrad(dy2d, x2d):
+def linear_wgrad(dy2d, x2d, with_bias_grad=False):
     M, N = dy2d.shape
     K = x2d.shape[1]
+    if with_bias_grad:
+        dw, db = conv2d_wgrad(dy2d.view(1, 1, M, N), x2d.view(1, 1, M, K), with_bias_grad=True)
+        return dw.view(N, K), db
     return conv2d_wgrad(dy2d.view(1, 1, M, N), x2d.view(1, 1, M, K)).view(N, K)

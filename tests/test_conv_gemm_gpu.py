@@ -72,6 +72,9 @@ def test_linear_backward(M, N, K):
     assert _report("wgrad", dw, dy.t() @ x) < TOL
     db = tc.colsum(dy)
     assert _report("colsum", db, dy.sum(0)) < 1e-4
+    dw2, db2 = tc.linear_wgrad(dy, x, with_bias_grad=True)      # bias gradient as a by-product of the wgrad launch
+    assert _report("wgrad (fused db)", dw2, dy.t() @ x) < TOL
+    assert _report("fused db", db2, dy.sum(0)) < 1e-4
 
 
 CONVS = [
@@ -126,6 +129,9 @@ def test_conv_forward_backward(cfg):
     dwp = tc.conv2d_wgrad(dy_nhwc, x_nhwc, scale, k, k, s, pad)
     dw = tc.unpack_wgrad(dwp, k, k)
     assert _report("wgrad", dw, wr.grad * scale.view(-1, 1, 1, 1)) < TOL
+    dwp2, db = tc.conv2d_wgrad(dy_nhwc, x_nhwc, scale, k, k, s, pad, with_bias_grad=True)
+    assert _report("wgrad (fused db)", tc.unpack_wgrad(dwp2, k, k), wr.grad * scale.view(-1, 1, 1, 1)) < TOL
+    assert _report("fused db", db, dy.sum((0, 2, 3))) < 1e-4
 
 
 @pytest.mark.parametrize("M,N,K,relu", [(550, 3, 256, False), (4400, 81, 256, True), (1000, 6, 256, False), (640, 256, 256, True)])
