@@ -107,6 +107,12 @@ int mdb_pack_conv_weight_f32(const float* w_oihw, const float* scale, float* w_p
                              void* stream);
 int mdb_unpack_conv_wgrad_f32(const float* dw_packed, float* dw_oihw, int O, int I, int taps, int accumulate,
                               void* stream);
+/* Multi-tensor forms of the two calls above: n tensors per call (one launch per 64); the array arguments are HOST arrays
+ * (scale may be NULL, or hold NULL entries). */
+int mdb_pack_conv_weights_multi_f32(int n, const float* const* w_oihw, const float* const* scale, float* const* w_packed,
+                                    const int* O, const int* I, const int* taps, void* stream);
+int mdb_unpack_conv_wgrads_multi_f32(int n, const float* const* dw_packed, float* const* dw_oihw, const int* O, const int* I,
+                                     const int* taps, void* stream);
 /* out[n] (+)= sum_m x[m][n]  (bias gradients) */
 int mdb_colsum_f32(const float* x, float* out, long long M, int N, int accumulate, void* stream);
 

@@ -30,6 +30,8 @@ SIGNATURES = {
     "mdb_conv2d_wgrad_bias_f32": [_PTR] * 5 + [c_int] * 10 + [_PTR],
     "mdb_pack_conv_weight_f32": [_PTR] * 3 + [c_int] * 3 + [_PTR],
     "mdb_unpack_conv_wgrad_f32": [_PTR] * 2 + [c_int] * 4 + [_PTR],
+    "mdb_pack_conv_weights_multi_f32": [c_int] + [_PTR] * 6 + [_PTR],
+    "mdb_unpack_conv_wgrads_multi_f32": [c_int] + [_PTR] * 5 + [_PTR],
     "mdb_colsum_f32": [_PTR] * 2 + [ctypes.c_longlong, c_int, c_int, _PTR],
     "mdb_attention_forward_f32": [_PTR] * 6 + [c_int] * 9 + [c_float, _PTR, ctypes.c_ulonglong, _PTR],
     "mdb_attention_backward_f32": [_PTR] * 11 + [c_int] * 12 + [c_float, _PTR, ctypes.c_ulonglong, _PTR],

@@ -117,11 +117,13 @@ class _ResNetFn(Function):
         del y
         # ---- bottlenecks ----------------------------------------------------------------------------------
         saved, packed, feats = [], [], []
+        # all bottleneck weights re-laid-out to [tap][O][I] with the BN scale folded in by ONE launch (52 tensors)
+        all_wp = [None] + tc.pack_weights_multi(list(weights[1:nconv]), list(scales[1:nconv]))
         ci = 1
         for bi, (stage, stride, has_ds, trainable) in enumerate(meta["blocks"]):
             idx = [ci, ci + 1, ci + 2] + ([ci + 3] if has_ds else [])
             ci += len(idx)
-            wp = [tc.pack_weight(weights[j].contiguous(), scales[j]) for j in idx]      # BN scale folded, RN-TF32
+            wp = [all_wp[j] for j in idx]
             o1 = tc.conv2d_forward(x, wp[0], shifts[idx[0]], None, 1, 1, 1, 0, relu=True, round_out=True)
             o2 = tc.conv2d_forward(o1, wp[1], shifts[idx[1]], None, 3, 3, stride, 1, relu=True, round_out=True)
             if has_ds:
@@ -158,6 +160,7 @@ class _ResNetFn(Function):
                 feat_of_block[k] = f
                 f += 1
         g = None                                                      # grad wrt block output, already ReLU-masked
+        pending = []                                                  # 3x3 weight gradients still in packed layout
         for k in range(len(blocks) - 1, -1, -1):
             stage, stride, has_ds, _ = blocks[k]
             x, o1, o2, out = ctx.saved[k]
@@ -170,7 +173,7 @@ class _ResNetFn(Function):
             grads[idx[2]] = tc.conv2d_wgrad(g, o2, sc[2], 1, 1, 1, 0).view_as(_w(ctx, idx[2]))
             g2 = tc.conv2d_dgrad(g, wp[2], o2.shape, None, o2, 1, 1, 1, 0, round_out=True)
             # conv2 (3x3, maybe strided)
-            grads[idx[1]] = tc.unpack_wgrad(tc.conv2d_wgrad(g2, o1, sc[1], 3, 3, stride, 1), 3, 3)
+            pending.append((idx[1], tc.conv2d_wgrad(g2, o1, sc[1], 3, 3, stride, 1)))   # 3x3: [tap][O][I] -> OIHW at the end
             g1 = tc.conv2d_dgrad(g2, wp[1], o1.shape, None, o1, 3, 3, stride, 1, round_out=True)
             # conv1
             grads[idx[0]] = tc.conv2d_wgrad(g1, x, sc[0], 1, 1, 1, 0).view_as(_w(ctx, idx[0]))
@@ -188,6 +191,8 @@ class _ResNetFn(Function):
             g = tc.conv2d_dgrad(g1, wp[0], x.shape, side, x, 1, 1, 1, 0, round_out=True)
             ctx.saved[k] = None
         ctx.saved = ctx.packed = None
+        for (j, _), dw in zip(pending, tc.unpack_wgrads_multi([d for _, d in pending], [(3, 3)] * len(pending))):
+            grads[j] = dw
         return (None, None) + tuple(grads)
 
 

@@ -42,6 +42,54 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __rest
     }
 }
 
+// Multi-tensor variants: one launch re-lays-out up to kMaxMulti weight tensors (a ResNet-50 has 52 conv weights and the
+// step is launch-count sensitive: ~5 us per tiny kernel).  blockIdx.y = tensor, the table travels as a kernel parameter.
+constexpr int kMaxMulti = 64;
+struct MultiTable {
+    const float* src[kMaxMulti];
+    const float* scale[kMaxMulti];
+    float* dst[kMaxMulti];
+    int O[kMaxMulti], I[kMaxMulti], taps[kMaxMulti];
+};
+
+__global__ void pack_weight_multi_kernel(const __grid_constant__ MultiTable tb, int round_tf32_out) {
+    const int k = blockIdx.y;
+    const float* __restrict__ w = tb.src[k];
+    const float* __restrict__ scale = tb.scale[k];
+    float* __restrict__ out = tb.dst[k];
+    const int O = tb.O[k], I = tb.I[k], taps = tb.taps[k];
+    const long long n = (long long)O * I * taps;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % I);
+        const long long r = i / I;
+        const int o = (int)(r % O);
+        const int t = (int)(r / O);
+        float v = w[((size_t)o * I + ci) * taps + t];
+        if (scale) v *= scale[o];
+        if (round_tf32_out) {
+            uint32_t rb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rb) : "f"(v));
+            v = __uint_as_float(rb);
+        }
+        out[i] = v;
+    }
+}
+
+__global__ void unpack_wgrad_multi_kernel(const __grid_constant__ MultiTable tb) {
+    const int k = blockIdx.y;
+    const float* __restrict__ dwp = tb.src[k];
+    float* __restrict__ dw = tb.dst[k];
+    const int O = tb.O[k], I = tb.I[k], taps = tb.taps[k];
+    const long long n = (long long)O * I * taps;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % taps);
+        const long long r = i / taps;
+        const int ci = (int)(r % I);
+        const int o = (int)(r / I);
+        dw[i] = dwp[((size_t)t * O + o) * I + ci];
+    }
+}
+
 // out[n] += sum_m x[m][n]; grid.x covers column groups of 32, grid.y row slabs.
 __global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long M, int N, int rows_per_block) {
     __shared__ float part[8][33];
@@ -85,6 +133,45 @@ int mdb_unpack_conv_wgrad_f32(const float* dw_packed, float* dw_oihw, int O, int
     const int grid = (int)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
     unpack_wgrad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(dw_packed, dw_oihw, O, I, taps, accumulate);
     return (int)cudaGetLastError();
+}
+
+// n tensors per call (any n: the call is cut into launches of <= 64 tensors); array arguments are HOST arrays.
+int mdb_pack_conv_weights_multi_f32(int n, const float* const* w_oihw, const float* const* scale, float* const* w_packed,
+                                    const int* O, const int* I, const int* taps, void* stream) {
+    if (n < 0 || (n > 0 && (!w_oihw || !w_packed || !O || !I || !taps))) return MDB_EINVAL;
+    for (int base = 0; base < n; base += kMaxMulti) {
+        MultiTable tb;
+        const int m = n - base < kMaxMulti ? n - base : kMaxMulti;
+        for (int k = 0; k < m; ++k) {
+            const int j = base + k;
+            if (!w_oihw[j] || !w_packed[j] || O[j] <= 0 || I[j] <= 0 || taps[j] <= 0) return MDB_EINVAL;
+            tb.src[k] = w_oihw[j]; tb.scale[k] = scale ? scale[j] : nullptr; tb.dst[k] = w_packed[j];
+            tb.O[k] = O[j]; tb.I[k] = I[j]; tb.taps[k] = taps[j];
+        }
+        pack_weight_multi_kernel<<<dim3(64, m), 256, 0, static_cast<cudaStream_t>(stream)>>>(tb, mdb_get_precision() == 0);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}
+
+int mdb_unpack_conv_wgrads_multi_f32(int n, const float* const* dw_packed, float* const* dw_oihw, const int* O, const int* I,
+                                     const int* taps, void* stream) {
+    if (n < 0 || (n > 0 && (!dw_packed || !dw_oihw || !O || !I || !taps))) return MDB_EINVAL;
+    for (int base = 0; base < n; base += kMaxMulti) {
+        MultiTable tb;
+        const int m = n - base < kMaxMulti ? n - base : kMaxMulti;
+        for (int k = 0; k < m; ++k) {
+            const int j = base + k;
+            if (!dw_packed[j] || !dw_oihw[j] || O[j] <= 0 || I[j] <= 0 || taps[j] <= 0) return MDB_EINVAL;
+            tb.src[k] = dw_packed[j]; tb.scale[k] = nullptr; tb.dst[k] = dw_oihw[j];
+            tb.O[k] = O[j]; tb.I[k] = I[j]; tb.taps[k] = taps[j];
+        }
+        unpack_wgrad_multi_kernel<<<dim3(64, m), 256, 0, static_cast<cudaStream_t>(stream)>>>(tb);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
 }
 
 int mdb_colsum_f32(const float* x, float* out, long long M, int N, int accumulate, void* stream_) {

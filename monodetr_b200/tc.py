@@ -2,6 +2,8 @@
 convolution / linear family").  Tensors are fp32 CUDA, activations NHWC, weights packed [tap][Cout][Cin].
 No fallback: a missing library or a failing launch raises RuntimeError.
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -37,6 +39,53 @@ def pack_weight(w_oihw, scale=None):
     _lib.check(_lib.lib().mdb_pack_conv_weight_f32(_p(w_oihw), _p(scale), _p(out), O, I, kh * kw, _s()), "pack_weight")
     _lib.count(1)
     return out
+
+
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+def _int_array(vals):
+    return (ctypes.c_int * len(vals))(*vals)
+
+
+def pack_weights_multi(weights, scales=None):
+    """[(O, I, kh, kw)] -> [(kh*kw, O, I)] in ONE launch per 64 tensors (views of one flat allocation)."""
+    n = len(weights)
+    if n == 0:
+        return []
+    scales = list(scales) if scales is not None else [None] * n
+    weights = [w.contiguous() for w in weights]
+    _chk(*weights, *scales)
+    sizes = [w.numel() for w in weights]
+    flat = torch.empty((sum(sizes),), dtype=torch.float32, device=weights[0].device)
+    outs, off = [], 0
+    for w, sz in zip(weights, sizes):
+        O, I, kh, kw = w.shape
+        outs.append(flat[off:off + sz].view(kh * kw, O, I))
+        off += sz
+    rc = _lib.lib().mdb_pack_conv_weights_multi_f32(
+        n, _ptr_array(weights), _ptr_array(scales), _ptr_array(outs), _int_array([w.shape[0] for w in weights]),
+        _int_array([w.shape[1] for w in weights]), _int_array([w.shape[2] * w.shape[3] for w in weights]), _s())
+    _lib.check(rc, "pack_weights_multi")
+    _lib.count((n + 63) // 64)
+    return outs
+
+
+def unpack_wgrads_multi(dw_packed_list, khw_list):
+    """[(taps, O, I)] -> [(O, I, kh, kw)] in ONE launch per 64 tensors."""
+    n = len(dw_packed_list)
+    if n == 0:
+        return []
+    _chk(*dw_packed_list)
+    outs = [torch.empty((d.shape[1], d.shape[2], kh, kw), dtype=torch.float32, device=d.device)
+            for d, (kh, kw) in zip(dw_packed_list, khw_list)]
+    rc = _lib.lib().mdb_unpack_conv_wgrads_multi_f32(
+        n, _ptr_array(dw_packed_list), _ptr_array(outs), _int_array([d.shape[1] for d in dw_packed_list]),
+        _int_array([d.shape[2] for d in dw_packed_list]), _int_array([d.shape[0] for d in dw_packed_list]), _s())
+    _lib.check(rc, "unpack_wgrads_multi")
+    _lib.count((n + 63) // 64)
+    return outs
 
 
 def unpack_wgrad(dw_packed, kh, kw):

@@ -161,3 +161,19 @@ def test_functional_linear_autograd_ragged_n(M, N, K, relu):
     assert _report("dx", gx, rx) < TOL
     assert _report("dw", gw, rw) < TOL
     assert _report("db", gb, rb) < TOL
+
+
+def test_multi_tensor_pack_unpack():
+    """One-launch re-layout of many conv weights / weight gradients == the per-tensor calls (bitwise)."""
+    from monodetr_b200 import tc
+    g = torch.Generator(device="cuda").manual_seed(7)
+    shapes = [(64, 64, 1, 1), (64, 64, 3, 3), (256, 64, 1, 1), (128, 128, 3, 3), (512, 256, 1, 1)] * 14    # 70 tensors: two launches
+    ws = [torch.randn(s, device="cuda", generator=g) for s in shapes]
+    scs = [torch.rand(s[0], device="cuda", generator=g) + 0.5 if i % 3 else None for i, s in enumerate(shapes)]
+    multi = tc.pack_weights_multi(ws, scs)
+    for w, sc, m in zip(ws, scs, multi):
+        assert torch.equal(m, tc.pack_weight(w, sc))
+    dws = [torch.randn(s[2] * s[3], s[0], s[1], device="cuda", generator=g) for s in shapes]
+    outs = tc.unpack_wgrads_multi(dws, [(s[2], s[3]) for s in shapes])
+    for d, s, o in zip(dws, shapes, outs):
+        assert torch.equal(o, tc.unpack_wgrad(d, s[2], s[3]))
