@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the MonoDETR hot path on B200 (see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload model|msda]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload model|msda|infer]
 
 Prints ONE JSON line (rank 0).  Workloads:
   model : full MonoDETR forward+backward, ResNet-50, 1280x384 synthetic images, train mode
@@ -332,7 +332,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("MDB_BENCH_WORKLOAD", "model"), choices=["model", "msda"])
+    ap.add_argument("--workload", default=os.environ.get("MDB_BENCH_WORKLOAD", "model"), choices=["model", "msda", "infer"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 8 at N=1, 16 at N>1 for model)")
     ap.add_argument("--lq", type=int, default=10200)
     ap.add_argument("--uniform-loc", action="store_true")
@@ -357,8 +357,8 @@ def main():
         line = run_msda_b200(args, rank, local_rank, ws)
     else:
         from monodetr_b200 import bench_model
-        line = bench_model.run(args, rank, local_rank, ws)
-        if line is not None and ws == 1:
+        line = bench_model.run(args, rank, local_rank, ws, infer=(args.workload == "infer"))
+        if line is not None and ws == 1 and args.workload == "model":
             line["cpu_baseline"] = cpu_baseline_model()
     if line is not None:
         print(json.dumps(line), flush=True)

@@ -1,4 +1,5 @@
-"""One eager train step of the model under `ncu --profile-from-start off` (cudaProfilerStart/Stop around step 2)."""
+"""One eager step of the model under `ncu --profile-from-start off` (cudaProfilerStart/Stop around step 2).
+usage: profile_step.py [batch] [train|infer]   (infer = eval-mode forward only, BASELINE configs[4] uses batch 32)"""
 import os
 import sys
 
@@ -14,11 +15,16 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 tc.set_precision(os.environ.get("MDB_PRECISION", "tf32x3"))
 torch.manual_seed(0)
 model, _ = build_monodetr(DEFAULT_MODEL_CFG)
-model = model.cuda().train()
+INFER = len(sys.argv) > 2 and sys.argv[2] == "infer"
+model = model.cuda().eval() if INFER else model.cuda().train()
 images, calibs, sizes = (t.cuda() for t in synthetic_batch(B, 1))
 
 
 def step():
+    if INFER:
+        with torch.no_grad():
+            surrogate_loss(model(images, calibs, None, sizes))
+        return
     for p in model.parameters():
         p.grad = None
     K.advance_seed(images.device)
