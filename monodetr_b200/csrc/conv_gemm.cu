@@ -41,7 +41,7 @@ constexpr int kEpiWarps = 4;               // epilogue warps of the 3xTF32 kerne
 
 struct TcParams {
     // ---- fprop / dgrad: decomposition of the M dimension into th x tw pixel rectangles ----------
-    int tiles_x, tiles_y, tw, th;
+    int tiles_x, tiles_y, tw, th, tb;   // an M tile = tw x th pixels of tb consecutive images (tw * th * tb == 128)
     int Ho, Wo;                      // logical output grid covered by tiles (bounds for rows)
     int out_sy, out_sx, out_oy, out_ox, out_H, out_W;   // real output pixel = (y*out_sy+out_oy, ...)
     int in_sy, in_sx;                // A-box origin = (y0*in_sy + dy[tap], x0*in_sx + dx[tap])
@@ -119,8 +119,9 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         if constexpr (MODE == 0) {
             const int per_img = p.tiles_x * p.tiles_y;
             t.iters = p.ntaps * p.cblocks;
-            t.img = r / per_img;
-            r -= t.img * per_img;
+            const int grp = r / per_img;
+            t.img = grp * p.tb;
+            r -= grp * per_img;
             t.y0 = (r / p.tiles_x) * p.th;
             t.x0 = (r % p.tiles_x) * p.tw;
         } else {
@@ -368,11 +369,12 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 const int row = q * 32 + i * 4 + r4;
                 rsc[i] = 1.f;
                 if constexpr (MODE == 0) {
-                    const int ly = row / p.tw, lx = row - ly * p.tw;
-                    const int y = t.y0 + ly, x = t.x0 + lx;
-                    if ((y < p.Ho) && (x < p.Wo)) rok |= 1u << i;
+                    const int lyt = row / p.tw, lx = row - lyt * p.tw;
+                    const int ib = lyt / p.th, ly = lyt - ib * p.th;       // image within the tile, row within the image
+                    const int y = t.y0 + ly, x = t.x0 + lx, img = t.img + ib;
+                    if ((y < p.Ho) && (x < p.Wo) && (img < p.n_img)) rok |= 1u << i;
                     const int oy = y * p.out_sy + p.out_oy, ox = x * p.out_sx + p.out_ox;
-                    roff[i] = (uint32_t)(((t.img * p.out_H + oy) * p.out_W + ox) * p.ldo);
+                    roff[i] = (uint32_t)(((img * p.out_H + oy) * p.out_W + ox) * p.ldo);
                 } else {
                     if ((t.m0 + row) < p.Mo_rows) {
                         rok |= 1u << i;
@@ -609,6 +611,20 @@ void pick_tile(int W, int H, int n_pix, int* tw, int* th) {
     *th = n_pix / best_tw;
 }
 
+// M tile of fprop / dgrad: tw x th pixels of tb consecutive images, tw * th * tb == n_pix (128).  Spanning images keeps
+// small feature maps dense (12 x 40 with 8 images: 8x4 pixels x 4 images = 30 full tiles instead of 40 tiles at 75 %).
+void pick_tile3(int W, int H, int B, int n_pix, int* tw, int* th, int* tb) {
+    long long best = -1;
+    *tw = n_pix; *th = 1; *tb = 1;
+    for (int b = 1; b <= n_pix; b <<= 1)
+        for (int w = n_pix / b; w >= 1; w >>= 1) {
+            const int h = n_pix / b / w;
+            if (b > 1 && b >= 2 * B) continue;                    // never more padding images than real ones
+            const long long cov = (long long)((W + w - 1) / w) * w * ((H + h - 1) / h) * h * ((B + b - 1) / b) * b;
+            if (best < 0 || cov < best) { best = cov; *tw = w; *th = h; *tb = b; }   // ties: fewer images, wider rows
+        }
+}
+
 struct ConvGeom {
     int B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo;
 };
@@ -644,11 +660,17 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
     if (rc) return rc;
     if (!x || !w_packed || !y) return MDB_EINVAL;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (kh == 1 && stride == 1 && pad == 0) {     // pointwise: the batch of images is one long row of pixels (no tile waste)
+        W = B * H * W; H = 1; B = 1;
+        g = ConvGeom{B, H, W, Cin, Cout, kh, kw, stride, pad, H, W};
+    }
     TcParams p;
     memset(&p, 0, sizeof(p));
-    pick_tile(g.Wo, g.Ho, BM, &p.tw, &p.th);
+    pick_tile3(g.Wo, g.Ho, B, BM, &p.tw, &p.th, &p.tb);
     p.tiles_x = (g.Wo + p.tw - 1) / p.tw;
     p.tiles_y = (g.Ho + p.th - 1) / p.th;
+    p.n_img = B;
+    const int n_groups = (B + p.tb - 1) / p.tb;
     p.Ho = g.Ho; p.Wo = g.Wo;
     p.out_sy = p.out_sx = 1; p.out_oy = p.out_ox = 0; p.out_H = g.Ho; p.out_W = g.Wo;
     p.in_sy = p.in_sx = stride;
@@ -667,7 +689,7 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
     {   // A: x as (C, W, H, B), box (32, tw*s, th*s, 1), element strides (1, s, s, 1)
         uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
         uint64_t str[4] = {1, (uint64_t)Cin, (uint64_t)W * Cin, (uint64_t)H * W * Cin};
-        uint32_t box[4] = {BK, (uint32_t)(p.tw * stride), (uint32_t)(p.th * stride), 1};
+        uint32_t box[4] = {BK, (uint32_t)(p.tw * stride), (uint32_t)(p.th * stride), (uint32_t)p.tb};
         uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
         if (box[1] > 256 || box[2] > 256) return MDB_EUNSUPPORTED;
         rc = make_map(&ma, x, 4, dims, str, box, es);
@@ -678,7 +700,7 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
     // 3xTF32: a 128x256 tile needs 96 KB per stage -> only 2 stages fit, which cannot hide DRAM latency; it pays off
     // only when the A operand is re-read from L2 (multi-tap convolutions), measured +6 % on 3x3 256->256.
     const bool wide = (g_precision == 0 || (wide_split && kh * kw > 1)) && (Cout % 256 == 0) &&
-                      ((long long)B * p.tiles_x * p.tiles_y * (Cout / 256) >= 100);
+                      ((long long)n_groups * p.tiles_x * p.tiles_y * (Cout / 256) >= 100);
     const int bn = wide ? 256 : (Cout <= 64 ? 64 : 128);
     {   // B: packed weights as (Cin, Cout, taps), box (32, BN, 1)
         uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
@@ -687,7 +709,7 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
         rc = make_map(&mb, w_packed, 3, dims, str, box, nullptr);
         if (rc) return rc;
     }
-    dim3 grid((Cout + bn - 1) / bn, B * p.tiles_x * p.tiles_y, 1);
+    dim3 grid((Cout + bn - 1) / bn, n_groups * p.tiles_x * p.tiles_y, 1);
     static const bool tmem_a = getenv("MDB_NO_TMEM_A") == nullptr;            // A/B switch (profiling)
     if (bn == 64) return (g_precision == 1) ? (tmem_a ? launch_tc<64, 6, 0, false, true, true>(ma, mb, p, grid, stream)
                                                       : launch_tc<64, 4, 0, false, true>(ma, mb, p, grid, stream))
@@ -708,6 +730,10 @@ int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* re
     if (rc) return rc;
     if (!dy || !w_packed || !dx) return MDB_EINVAL;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (kh == 1 && stride == 1 && pad == 0) {     // pointwise: one long row of pixels
+        W = B * H * W; H = 1; B = 1;
+        g = ConvGeom{B, H, W, Cin, Cout, kh, kw, stride, pad, H, W};
+    }
     // dx[y,x] = sum_{ky,kx} dy[(y+pad-ky)/s, (x+pad-kx)/s] * W[ky,kx]  where the division is exact.
     // Per output parity class (py,px) (only one class for s == 1) the contributing taps are fixed and the
     // dy access is a unit-stride shifted box: oy = (y + pad - ky)/s = j + (py + pad - ky)/s  for y = s*j + py.
@@ -717,9 +743,11 @@ int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* re
             memset(&p, 0, sizeof(p));
             const int Hc = (H - py + stride - 1) / stride, Wc = (W - px + stride - 1) / stride;  // pixels in class
             if (Hc <= 0 || Wc <= 0) continue;
-            pick_tile(Wc, Hc, BM, &p.tw, &p.th);
+            pick_tile3(Wc, Hc, B, BM, &p.tw, &p.th, &p.tb);
             p.tiles_x = (Wc + p.tw - 1) / p.tw;
             p.tiles_y = (Hc + p.th - 1) / p.th;
+            p.n_img = B;
+            const int n_groups = (B + p.tb - 1) / p.tb;
             p.Ho = Hc; p.Wo = Wc;
             p.out_sy = p.out_sx = stride; p.out_oy = py; p.out_ox = px; p.out_H = H; p.out_W = W;
             p.in_sy = p.in_sx = 1;
@@ -744,7 +772,7 @@ int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* re
             {   // A: dy as (Cout, Wo, Ho, B), unit stride
                 uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)g.Wo, (uint64_t)g.Ho, (uint64_t)B};
                 uint64_t str[4] = {1, (uint64_t)Cout, (uint64_t)g.Wo * Cout, (uint64_t)g.Ho * g.Wo * Cout};
-                uint32_t box[4] = {BK, (uint32_t)p.tw, (uint32_t)p.th, 1};
+                uint32_t box[4] = {BK, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tb};
                 rc = make_map(&ma, dy, 4, dims, str, box, nullptr);
                 if (rc) return rc;
             }
@@ -755,7 +783,7 @@ int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* re
                 rc = make_map(&mb, w_packed, 3, dims, str, box, nullptr, true);
                 if (rc) return rc;
             }
-            dim3 grid((Cin + 127) / 128, B * p.tiles_x * p.tiles_y, 1);
+            dim3 grid((Cin + 127) / 128, n_groups * p.tiles_x * p.tiles_y, 1);
             if (nt == 0) {   // no tap reaches this parity class (1x1 stride 2): result = (0 + residual) * mask
                 p.ntaps = 0;
             }
@@ -785,6 +813,10 @@ int mdb_conv2d_wgrad_bias_f32(const float* dy, const float* x, const float* rows
     if (rc) return rc;
     if (!dy || !x || !dw_packed) return MDB_EINVAL;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (kh == 1 && stride == 1 && pad == 0) {     // pointwise: one long row of pixels (full 32-pixel reduction tiles)
+        W = B * H * W; H = 1; B = 1;
+        g = ConvGeom{B, H, W, Cin, Cout, kh, kw, stride, pad, H, W};
+    }
     const int taps = kh * kw;
     static const bool tmem_a = getenv("MDB_NO_TMEM_A") == nullptr;
     const bool fused_db = db && g_precision == 1 && tmem_a;
