@@ -49,6 +49,8 @@ struct TcParams {
     int tap_dy[kMaxTaps], tap_dx[kMaxTaps], tap_w[kMaxTaps];
     // ---- wgrad: reduction over pixel tiles of 32 (rth x rtw), split across blockIdx.z ----------
     int rtiles_x, rtiles_y, rtw, rth, n_img, red_per_split;
+    // ---- fprop split-K (few tiles, very long reduction): slice z of the k-blocks writes its partial tile to out + z * slice_stride
+    int kb_per_slice, slice_stride;  // 0 = off; a fixed-order reduction kernel sums the slices (deterministic, unlike atomics)
     int total_tiles, n_tiles_n, n_tiles_m;   // persistent tile walk: tile = (z * n_tiles_m + m) * n_tiles_n + n
     int w_sy, w_sx, wg_taps, wg_kw, wg_pad;   // X-box origin = (y0*w_sy + ky - pad, x0*w_sx + kx - pad); all taps in ONE launch
     // ---- epilogue -----------------------------------------------------------------------------
@@ -110,15 +112,21 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int lane = threadIdx.x & 31;
 
     // ---- tile decode (identical in every role) -----------------------------------------------------
-    struct Tile { int n0, img, y0, x0, m0, red_begin, iters, tap; };
+    struct Tile { int n0, img, y0, x0, m0, red_begin, iters, tap, slice; };
     auto decode = [&](int tix) {
         Tile t;
         t.n0 = (tix % p.n_tiles_n) * BN;
         int r = tix / p.n_tiles_n;
-        t.img = t.y0 = t.x0 = t.m0 = t.red_begin = t.tap = 0;
+        t.img = t.y0 = t.x0 = t.m0 = t.red_begin = t.tap = t.slice = 0;
         if constexpr (MODE == 0) {
             const int per_img = p.tiles_x * p.tiles_y;
             t.iters = p.ntaps * p.cblocks;
+            if (p.kb_per_slice > 0) {
+                t.slice = r / p.n_tiles_m;
+                r -= t.slice * p.n_tiles_m;
+                t.red_begin = t.slice * p.kb_per_slice;
+                t.iters = max(0, min(t.iters, t.red_begin + p.kb_per_slice) - t.red_begin);
+            }
             const int grp = r / per_img;
             t.img = grp * p.tb;
             r -= grp * per_img;
@@ -172,8 +180,9 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     uint8_t* b_dst = a_dst + kTileABytes;
                     mbar_arrive_expect_tx(&full_bar[s], kRawBytes);
                     if constexpr (MODE == 0) {
-                        const int tap = it / p.cblocks;
-                        const int cb = it - tap * p.cblocks;
+                        const int kit = t.red_begin + it;                 // (fprop split-K: this slice's first k-block)
+                        const int tap = kit / p.cblocks;
+                        const int cb = kit - tap * p.cblocks;
                         tma_load_4d(a_dst, &mapA, &full_bar[s], cb * BK, t.x0 * p.in_sx + p.tap_dx[tap],
                                     t.y0 * p.in_sy + p.tap_dy[tap], t.img);
                         if constexpr (!B_MN) {
@@ -374,7 +383,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     const int y = t.y0 + ly, x = t.x0 + lx, img = t.img + ib;
                     if ((y < p.Ho) && (x < p.Wo) && (img < p.n_img)) rok |= 1u << i;
                     const int oy = y * p.out_sy + p.out_oy, ox = x * p.out_sx + p.out_ox;
-                    roff[i] = (uint32_t)(((img * p.out_H + oy) * p.out_W + ox) * p.ldo);
+                    roff[i] = (uint32_t)(((img * p.out_H + oy) * p.out_W + ox) * p.ldo + t.slice * p.slice_stride);
                 } else {
                     if ((t.m0 + row) < p.Mo_rows) {
                         rok |= 1u << i;
@@ -598,6 +607,34 @@ int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, dim3 grid,
     return (int)cudaGetLastError();
 }
 
+// fprop split-K, second pass: y[i] = bias[i % N] + sum_z ws[z][i] in a fixed order.
+__global__ void splitk_reduce_kernel(const float4* __restrict__ ws, const float4* __restrict__ bias, float4* __restrict__ y,
+                                     long long n4, int N4, int slices, long long stride4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 a = bias ? bias[i % N4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < slices; ++z) {
+            const float4 v = ws[z * stride4 + i];
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        y[i] = a;
+    }
+}
+
+// Scratch for the split-K partial tiles: grown outside stream capture only (the eager warm-up steps size it).
+float* g_splitk_ws = nullptr;
+size_t g_splitk_ws_bytes = 0;
+int splitk_workspace(size_t bytes, float** out) {
+    if (bytes > g_splitk_ws_bytes) {
+        if (g_splitk_ws) cudaFree(g_splitk_ws);
+        g_splitk_ws = nullptr; g_splitk_ws_bytes = 0;
+        cudaError_t e = cudaMalloc(&g_splitk_ws, bytes);
+        if (e != cudaSuccess) return (int)e;
+        g_splitk_ws_bytes = bytes;
+    }
+    *out = g_splitk_ws;
+    return 0;
+}
+
 // choose a th x tw rectangle with th*tw == n_pix (128 for M tiles, 32 for wgrad reduction tiles)
 void pick_tile(int W, int H, int n_pix, int* tw, int* th) {
     int best_tw = n_pix, best_waste = 1 << 30;
@@ -711,6 +748,36 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
     }
     dim3 grid((Cout + bn - 1) / bn, n_groups * p.tiles_x * p.tiles_y, 1);
     static const bool tmem_a = getenv("MDB_NO_TMEM_A") == nullptr;            // A/B switch (profiling)
+    // Split-K for a handful of tiles with a very long reduction (the 3x3 stride-2 2048->256 neck convolution: 16-32 tiles x
+    // 576 k-blocks kept a fifth of the SMs busy for 0.3 ms).  Slices write partial tiles to a scratch buffer and a second
+    // kernel adds them in a fixed order (+ bias): bit-reproducible, unlike atomic accumulation.
+    {
+        const int tiles = (int)(grid.x * grid.y), kblocks = p.ntaps * p.cblocks, sms = num_sms_tc();
+        const long long out_elems = (long long)B * g.Ho * g.Wo * Cout;
+        if (g_precision == 1 && tmem_a && bn == 128 && tiles * 2 <= sms && kblocks >= 256 && !residual && !p.relu && Cout % 4 == 0 &&
+            (reinterpret_cast<uintptr_t>(bias) & 15u) == 0) {
+            // fixed slice length, and only reductions so long (>= 256 k-blocks) that every sane batch size takes this path:
+            // the summation order must not depend on the batch size (same image -> same bits for B = 1 or 8)
+            p.kb_per_slice = 32;
+            const int slices = (kblocks + p.kb_per_slice - 1) / p.kb_per_slice;
+            if (out_elems * slices < (1ll << 31)) {
+                float* ws = nullptr;
+                rc = splitk_workspace(sizeof(float) * (size_t)out_elems * slices, &ws);
+                if (rc) return rc;
+                p.slice_stride = (int)out_elems;
+                p.out = ws; p.bias = nullptr;
+                grid.z = slices;
+                rc = launch_tc<128, 4, 0, false, true, true>(ma, mb, p, grid, stream);
+                if (rc) return rc;
+                const long long n4 = out_elems / 4;
+                const int blocks = (int)((n4 + 255) / 256 > 1184 ? 1184 : (n4 + 255) / 256);
+                splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(ws), reinterpret_cast<const float4*>(bias),
+                                                                 reinterpret_cast<float4*>(y), n4, Cout / 4, slices, n4);
+                return (int)cudaGetLastError();
+            }
+            p.kb_per_slice = 0;
+        }
+    }
     if (bn == 64) return (g_precision == 1) ? (tmem_a ? launch_tc<64, 6, 0, false, true, true>(ma, mb, p, grid, stream)
                                                       : launch_tc<64, 4, 0, false, true>(ma, mb, p, grid, stream))
                                             : launch_tc<64, 6, 0, false, false>(ma, mb, p, grid, stream);
@@ -841,11 +908,15 @@ int mdb_conv2d_wgrad_bias_f32(const float* dy, const float* x, const float* rows
     const int total_red = B * p.rtiles_x * p.rtiles_y;
     const int bn = (g_precision == 0 && Cin >= 256) ? 256 : 128;
     const int tiles = ((Cout + BM - 1) / BM) * ((Cin + bn - 1) / bn) * taps;
-    // split-K over pixel tiles: enough CTAs to fill the machine (~2 waves), but at least ~24 reduction steps per CTA so
-    // the 128 x BN atomic epilogue stays a small fraction of the work.
-    int splits = (2 * num_sms_tc() + tiles - 1) / tiles;
-    const int max_splits = total_red / 24 > 0 ? total_red / 24 : 1;
-    if (splits > max_splits) splits = max_splits;
+    // split-K over pixel tiles.  Large problems: ~2 waves of CTAs, but at least ~24 reduction steps per CTA so the
+    // 128 x BN atomic epilogue stays a small fraction of the work.  Small problems (decoder / head linears, M = 4400 rows
+    // = 138 steps): the launch is latency-bound, so spread it over up to one wave with >= 8 steps per CTA (measured
+    // 23 us -> ~10 us per launch, ~200 such launches per step).
+    const int sms = num_sms_tc();
+    int big = (2 * sms + tiles - 1) / tiles, small = sms / tiles;
+    if (big > total_red / 24) big = total_red / 24;
+    if (small > total_red / 8) small = total_red / 8;
+    int splits = big > small ? big : small;
     if (splits < 1) splits = 1;
     p.red_per_split = (total_red + splits - 1) / splits;
     splits = (total_red + p.red_per_split - 1) / p.red_per_split;
