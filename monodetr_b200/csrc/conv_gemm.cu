@@ -11,10 +11,11 @@
 // depthaware_transformer.py:339-343,467-473 FFN / decoder linears).
 //
 // Layouts: activations NHWC fp32 [B][H][W][C]; packed weights [tap][Cout][Cin]; output NHWC.
-// Tile: 128 output pixels (a th x tw rectangle of one image) x BN output channels, K step = 32 fp32
-// (one 128-byte swizzle span).  Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
-// issuer (one elected lane), warps 2-5 = epilogue (TMEM -> registers -> fused bias / residual /
-// ReLU / ReLU-mask / row-scale -> global).  smem ring of STAGES stages, mbarrier full/empty pairs.
+// Tile: 128 output pixels (tw x th pixels of tb consecutive images) x BN output channels, K step = 32 fp32
+// (one 128-byte swizzle span).  Persistent CTAs (one per SM) walk the tiles.  Warp roles: warp 0 = TMA producer,
+// warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2-5 = 3xTF32 splitter (default precision; they also
+// move the A tile into tensor memory), last 4 warps = epilogue (TMEM -> registers -> smem transpose -> fused bias /
+// residual / ReLU / ReLU-mask / row-scale -> global).  smem ring of STAGES stages, mbarrier full/empty pairs.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -74,6 +75,7 @@ struct TcParams {
 //   warps 2-5       (SPLIT only) splitter warps: error-compensated "3xTF32".  For every landed stage they write
 //                   lo = x - trunc_tf32(x) of both tiles next to the raw tiles; the MMA warp then issues
 //                   A*B + A_lo*B + A*B_lo (the tensor core truncates the raw fp32 bits itself) = ~fp32 accuracy.
+//                   With TA (default) the A tile and its lo part go to TENSOR MEMORY instead (see kStageBytes below).
 template <int BN, int STAGES, int MODE /*0 fprop/dgrad, 1 wgrad*/, bool B_MN, bool SPLIT, bool TA = false>
 __global__ void __launch_bounds__(SPLIT ? 192 + 32 * kEpiWarps : 192)
 tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
