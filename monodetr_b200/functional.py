@@ -4,6 +4,8 @@ PyTorch/CPU fallback).  Activations are channels-last: images NHWC, token tensor
 Dropout sites are identified by an integer `site`; masks are regenerated in backward from the device seed
 (kernels.seed_tensor), so nothing but the seed is kept.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 from torch.autograd import Function
@@ -23,6 +25,31 @@ def _p(t):
 
 def _pad4(n):
     return (n + 3) // 4 * 4
+
+
+# ---- fork/join onto a side stream for small, mutually independent launches --------------------------------------
+# The data-gradient and the weight-gradient GEMM of a small linear layer (decoder / heads: 4400 rows) occupy 30-70 of the
+# 148 SMs for ~10 us each and do not depend on each other: the weight gradient runs on a side stream while the main
+# stream computes the data gradient, and the main stream waits for it before the function returns (so autograd and the
+# caching allocator only ever see completed results; under CUDA-graph capture this is the ordinary fork/join pattern).
+_SIDE_STREAMS = {}
+_SIDE_MAX_ROWS = 0 if os.environ.get("MDB_NO_SIDE_STREAM") else 8192
+
+
+class _Fork:
+    def __init__(self):
+        dev = torch.cuda.current_device()
+        self.main = torch.cuda.current_stream()
+        self.side = _SIDE_STREAMS.get(dev)
+        if self.side is None:
+            self.side = _SIDE_STREAMS[dev] = torch.cuda.Stream(dev)
+        self.side.wait_stream(self.main)
+
+    def join(self, *tensors):
+        self.main.wait_stream(self.side)
+        for t in tensors:                     # allocated on the side stream, consumed (and freed) on the main stream
+            if t is not None:
+                t.record_stream(self.main)
 
 
 # ---- small raw wrappers ---------------------------------------------------------------------------------
@@ -96,18 +123,24 @@ class _Linear(Function):
             dy2 = F.pad(dy2, (0, Np - N))
             wr = F.pad(wr, (0, 0, 0, Np - N))
         dx = dw = db = dres = None
-        if ctx.needs_input_grad[0]:
-            dx = tc.linear_dgrad(dy2, wr).view(xshape)
         want_db = has_b and ctx.needs_input_grad[2]
+        fork = None
+        if ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and dy2.shape[0] <= _SIDE_MAX_ROWS:
+            fork = _Fork()                    # small layer: weight gradient on the side stream, data gradient on this one
         if ctx.needs_input_grad[1]:
-            if want_db:                       # bias gradient = by-product of the weight-gradient launch
-                dw, db = tc.linear_wgrad(dy2, x2, with_bias_grad=True)
-            else:
-                dw = tc.linear_wgrad(dy2, x2)
-            if Np != N:
-                dw = dw[:N]
+            with torch.cuda.stream(fork.side if fork else torch.cuda.current_stream()):
+                if want_db:                   # bias gradient = by-product of the weight-gradient launch
+                    dw, db = tc.linear_wgrad(dy2, x2, with_bias_grad=True)
+                else:
+                    dw = tc.linear_wgrad(dy2, x2)
         elif want_db:
             db = tc.colsum(dy2)
+        if ctx.needs_input_grad[0]:
+            dx = tc.linear_dgrad(dy2, wr).view(xshape)
+        if fork:
+            fork.join(dw, db)
+        if dw is not None and Np != N:
+            dw = dw[:N]
         if db is not None and Np != N:
             db = db[:N]
         if has_res and ctx.needs_input_grad[3]:
