@@ -1,24 +1,16 @@
 """CPU, world_size 2, gloo: the flat-bucket gradient all-reduce (monodetr_b200/ddp.py) -- host logic of the N>1 path."""
 import os
-import socket
+import tempfile
 
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
 
-def _free_port():
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    p = s.getsockname()[1]
-    s.close()
-    return p
-
-
-def _worker(rank, world, port, q, views):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+def _worker(rank, world, store_path, q, views):
+    # file rendezvous: no port to race for, nothing to resolve (gloo itself still binds 127.0.0.1)
+    os.environ["GLOO_SOCKET_IFNAME"] = "lo"
+    dist.init_process_group("gloo", init_method=f"file://{store_path}", rank=rank, world_size=world)
     from monodetr_b200.ddp import FlatGradBucket, broadcast_parameters
     torch.manual_seed(rank)                       # different init per rank -> broadcast must equalise
     model = torch.nn.ModuleDict({
@@ -42,6 +34,7 @@ def _worker(rank, world, port, q, views):
     expect = sum(gathered) / world
     ok = torch.allclose(bucket.flat, expect, atol=1e-6) and model["a"].weight.grad.data_ptr() == bucket.flat.data_ptr()
     q.put((rank, bool(ok), w0))
+    dist.barrier()                                # nobody tears its sockets down while the peer is still communicating
     dist.destroy_process_group()
 
 
@@ -52,11 +45,11 @@ import pytest
 def test_flat_bucket_allreduce_world2(views):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, views)) for r in range(2)]
+    store_path = os.path.join(tempfile.mkdtemp(prefix="mdb_gloo_"), "store")
+    procs = [ctx.Process(target=_worker, args=(r, 2, store_path, q, views)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in procs]
+    res = [q.get(timeout=600) for _ in procs]      # a cold `import torch` in a fresh container can take a minute
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
