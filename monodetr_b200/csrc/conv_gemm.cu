@@ -698,6 +698,7 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
     int rc = check_geom(g, true);
     if (rc) return rc;
     if (!x || !w_packed || !y) return MDB_EINVAL;
+    if ((unsigned long long)B * g.Ho * g.Wo * Cout >= (1ull << 32)) return MDB_EUNSUPPORTED;   // the epilogue indexes with 32 bits
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (kh == 1 && stride == 1 && pad == 0) {     // pointwise: the batch of images is one long row of pixels (no tile waste)
         W = B * H * W; H = 1; B = 1;
@@ -798,6 +799,7 @@ int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* re
     int rc = check_geom(g);
     if (rc) return rc;
     if (!dy || !w_packed || !dx) return MDB_EINVAL;
+    if ((unsigned long long)B * H * W * Cin >= (1ull << 32)) return MDB_EUNSUPPORTED;           // the epilogue indexes with 32 bits
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (kh == 1 && stride == 1 && pad == 0) {     // pointwise: one long row of pixels
         W = B * H * W; H = 1; B = 1;
