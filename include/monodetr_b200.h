@@ -78,7 +78,12 @@ int mdb_msda_prep_backward_f32(const float* dloc, const float* dattn, const floa
  * Activations are NHWC fp32: x[B][H][W][Cin], y[B][Ho][Wo][Cout]; weights are "packed"
  * [kh*kw][Cout][Cin] (mdb_pack_conv_weight_f32).  A linear layer y[M,N] = x[M,K] w[N,K]^T is the call
  * with B=1, H=1, W=M, Cin=K, Cout=N, kh=kw=1, stride=1, pad=0 (w itself is already "packed").
- * Supported: kh=kw in {1,3}, stride in {1,2}, Cin%4==0, Cout%4==0, 16-byte aligned pointers.
+ * Supported: kh=kw in {1,3}, stride in {1,2}, Cin%4==0, 16-byte aligned pointers; Cout%4==0 for dgrad / wgrad (the
+ * forward writes any Cout, e.g. the 3-class / 81-bin head widths of monodetr.py:102-117); outputs below 2^32 elements.
+ * Results do not depend on the batch size (same image -> same bits) and are bit-reproducible run to run for
+ * forward / dgrad; wgrad accumulates its split-K partial sums with fp32 atomics.  The one forward shape with
+ * >= 256 k-blocks and few tiles (3x3 stride-2 2048->256, monodetr.py:83-91) reduces through a scratch buffer that is
+ * grown with cudaMalloc on first use: run one eager step before capturing a CUDA graph.
  */
 /* Arithmetic of the tensor-core family: 1 (default) = error-compensated 3xTF32 (A*B + A_lo*B + A*B_lo, ~fp32 accuracy,
  * what the 1e-3 parity tests run); 0 = single-pass TF32 with round-to-nearest operands (cuDNN's allow_tf32 class). */
