@@ -21,8 +21,20 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "reference" in item.keywords and not have_ref:
             item.add_marker(skip_ref)
+    items.sort(key=_rank)                                   # stable: keeps the in-file order
 
 
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+# Run order for `pytest -x`: the parity suites of the path's own operators first (MSDA, tensor-core conv/linear, whole
+# model), host/oracle checks next, everything else after -- so that one late failure cannot hide the main parity evidence.
+_ORDER = ["test_msda_gpu", "test_msda_reference_generators_gpu", "test_conv_gemm_gpu", "test_elementwise_gpu",
+          "test_attn_norm_gpu", "test_model_gpu", "test_model_grad_gpu"]
+
+
+def _rank(item):
+    name = os.path.splitext(os.path.basename(str(item.fspath)))[0]
+    return _ORDER.index(name) if name in _ORDER else len(_ORDER)
