@@ -25,6 +25,7 @@ extern "C" {
 
 #define MDB_EINVAL (-1)      /* bad size / null pointer / misaligned pointer */
 #define MDB_EUNSUPPORTED (-2) /* shape outside what the kernels implement */
+#define MDB_EWORKSPACE (-3)   /* scratch buffer missing / too small: see mdb_set_workspace */
 
 /* Library/ABI version (bumped when a signature changes). */
 int mdb_abi_version(void);
@@ -79,16 +80,38 @@ int mdb_msda_prep_backward_f32(const float* dloc, const float* dattn, const floa
  * [kh*kw][Cout][Cin] (mdb_pack_conv_weight_f32).  A linear layer y[M,N] = x[M,K] w[N,K]^T is the call
  * with B=1, H=1, W=M, Cin=K, Cout=N, kh=kw=1, stride=1, pad=0 (w itself is already "packed").
  * Supported: kh=kw in {1,3}, stride in {1,2}, Cin%4==0, 16-byte aligned pointers; Cout%4==0 for dgrad / wgrad (the
- * forward writes any Cout, e.g. the 3-class / 81-bin head widths of monodetr.py:102-117); outputs below 2^32 elements.
+ * forward writes any Cout, e.g. the 3-class / 81-bin head widths of monodetr.py:102-117); outputs below 2^31 elements.
  * Results do not depend on the batch size (same image -> same bits) and are bit-reproducible run to run for
  * forward / dgrad; wgrad accumulates its split-K partial sums with fp32 atomics.  The one forward shape with
- * >= 256 k-blocks and few tiles (3x3 stride-2 2048->256, monodetr.py:83-91) reduces through a scratch buffer that is
- * grown with cudaMalloc on first use: run one eager step before capturing a CUDA graph.
+ * >= 256 k-blocks and few tiles (3x3 stride-2 2048->256, monodetr.py:83-91) reduces through the scratch buffer the caller
+ * registers with mdb_set_workspace (per device; the library itself never allocates or frees device memory).
  */
-/* Arithmetic of the tensor-core family: 1 (default) = error-compensated 3xTF32 (A*B + A_lo*B + A*B_lo, ~fp32 accuracy,
- * what the 1e-3 parity tests run); 0 = single-pass TF32 with round-to-nearest operands (cuDNN's allow_tf32 class). */
+/* Arithmetic of the tensor-core family (a process-wide numerical setting): 1 = error-compensated 3xTF32 (A*B + A_lo*B +
+ * A*B_lo, ~fp32 accuracy); 0 = single-pass TF32 with round-to-nearest operands (cuDNN's allow_tf32 class); 2 = error-
+ * compensated BF16x3 for forward / dgrad (operands split into bf16 hi + lo, same three products at twice the tensor rate,
+ * relative error ~2^-17 per product; weights arrive pre-split through mdb_pack_gemm_weights_bf16x3 and the *_bf16x3 entry
+ * points; the _f32 entry points and wgrad run 3xTF32 in this mode). */
 int mdb_set_precision(int mode);
 int mdb_get_precision(void);
+/* Split-K scratch of mdb_conv2d_forward_* for the CURRENT device (cudaGetDevice): the library never allocates device
+ * memory.  Ask _workspace_bytes (0 = none needed; negative = MDB_E*), register a buffer at least that large that stays
+ * valid while launches (or captured CUDA graphs) may use it; otherwise those shapes return MDB_EWORKSPACE. */
+int mdb_set_workspace(void* buf, unsigned long long bytes);
+long long mdb_conv2d_forward_workspace_bytes(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
+                                             int flags, int has_residual, int split_weights);
+/* Precision mode 2: weights split once per step into bf16 (hi, lo) pairs.  wf[tap][Cout][ceil(Cin/32)][hi 32 | lo 32] is the
+ * forward operand, wd[tap][Cin][ceil(Cout/32)][hi 32 | lo 32] (the transposed weight) the dgrad operand; sizes in bf16
+ * elements: taps*Cout*ceil(Cin/32)*64 and taps*Cin*ceil(Cout/32)*64.  n tensors per call, HOST arrays; scale (FrozenBN
+ * fold, backbone.py:54-64) and wd may be NULL or hold NULL entries.  src_packed: 0 = OIHW sources (nn.Conv2d / nn.Linear
+ * weights as stored), 1 = [tap][Cout][Cin] sources.  taps <= 9. */
+int mdb_pack_gemm_weights_bf16x3(int n, const float* const* w, const float* const* scale, void* const* wf, void* const* wd,
+                                 const int* O, const int* I, const int* taps, int src_packed, void* stream);
+int mdb_conv2d_forward_bf16x3(const float* x, const void* w_split, const float* bias, const float* residual, float* y,
+                              int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int flags,
+                              void* stream);
+int mdb_conv2d_dgrad_bf16x3(const float* dy, const void* w_split_t, const float* residual, const float* relu_mask,
+                            float* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
+                            int flags, void* stream);
 int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* bias /*[Cout]|NULL*/,
                            const float* residual /*like y|NULL*/, float* y,
                            int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,

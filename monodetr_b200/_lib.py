@@ -25,6 +25,11 @@ SIGNATURES = {
     "mdb_set_precision": [c_int],
     "mdb_get_precision": [],
     "mdb_conv2d_forward_f32": [_PTR] * 5 + [c_int] * 10 + [_PTR],
+    "mdb_conv2d_forward_bf16x3": [_PTR] * 5 + [c_int] * 10 + [_PTR],
+    "mdb_conv2d_dgrad_bf16x3": [_PTR] * 5 + [c_int] * 10 + [_PTR],
+    "mdb_conv2d_forward_workspace_bytes": [c_int] * 12,
+    "mdb_set_workspace": [_PTR, ctypes.c_ulonglong],
+    "mdb_pack_gemm_weights_bf16x3": [c_int] + [_PTR] * 7 + [c_int, _PTR],
     "mdb_conv2d_dgrad_f32": [_PTR] * 5 + [c_int] * 10 + [_PTR],
     "mdb_conv2d_wgrad_f32": [_PTR] * 4 + [c_int] * 10 + [_PTR],
     "mdb_conv2d_wgrad_bias_f32": [_PTR] * 5 + [c_int] * 10 + [_PTR],
@@ -47,7 +52,7 @@ SIGNATURES = {
     "mdb_depth_sample_forward_f32": [_PTR] * 3 + [c_int] * 4 + [_PTR],
     "mdb_depth_sample_backward_f32": [_PTR] * 3 + [c_int] * 4 + [_PTR],
 }
-_RESTYPES = {"mdb_error_string": ctypes.c_char_p}
+_RESTYPES = {"mdb_error_string": ctypes.c_char_p, "mdb_conv2d_forward_workspace_bytes": ctypes.c_longlong}
 
 
 def lib():

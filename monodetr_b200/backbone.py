@@ -118,7 +118,10 @@ class _ResNetFn(Function):
         # ---- bottlenecks ----------------------------------------------------------------------------------
         saved, packed, feats = [], [], []
         # all bottleneck weights re-laid-out to [tap][O][I] with the BN scale folded in by ONE launch (52 tensors)
-        all_wp = [None] + tc.pack_weights_multi(list(weights[1:nconv]), list(scales[1:nconv]))
+        if tc.get_precision() == "bf16x3":      # (hi, lo) bf16 operands for fprop and dgrad, BN scale folded before the split
+            all_wp = [None] + tc.split_weights([w.detach() for w in weights[1:nconv]], list(scales[1:nconv]))
+        else:
+            all_wp = [None] + tc.pack_weights_multi(list(weights[1:nconv]), list(scales[1:nconv]))
         ci = 1
         for bi, (stage, stride, has_ds, trainable) in enumerate(meta["blocks"]):
             idx = [ci, ci + 1, ci + 2] + ([ci + 3] if has_ds else [])

@@ -89,7 +89,6 @@ def run(args, rank, local_rank, ws, infer=False):
                 loss_buf.copy_(surrogate_loss(out))          # checksum over every output head = the step's result
             return
         bucket.zero()
-        K.advance_seed(dev)
         out = model(images, calibs, None, sizes)
         loss = surrogate_loss(out)
         loss.backward()
@@ -221,13 +220,14 @@ def run(args, rank, local_rank, ws, infer=False):
     line = {
         "metric": "images/sec (1280x384, fwd only)" if infer else METRIC, "value": B * ws * args.steps / (total_ms * 1e-3), "unit": "images/sec", "n_gpus": ws,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == "tf32x3" else "tf32",
+        "scaling": "weak", "vs_baseline": None, "dtype": {"tf32x3": "f32 (3xTF32)", "bf16x3": "f32 (BF16x3 fprop/dgrad, 3xTF32 wgrad)", "tf32": "tf32"}[precision],
         "data": "synthetic",
         "config": {"workload": (f"MonoDETR inference forward, ResNet-50, batch {B}/GPU, 1280x384 synthetic, eval mode (50 queries), "
                                 f"{'independent replicas, ' if ws > 1 else ''}fp32 storage, tensor-core math = " if infer else
                                 f"full MonoDETR fwd+bwd, ResNet-50, batch {B}/GPU, 1280x384 synthetic, train mode (550 queries, dropout 0.1), "
                                 f"surrogate loss, {'flat-bucket NCCL all-reduce, ' if ws > 1 else ''}fp32 storage, tensor-core math = ")
-                               + ("error-compensated 3xTF32 (fp32-equivalent)" if precision == "tf32x3" else "single-pass TF32"),
+                               + {"tf32x3": "error-compensated 3xTF32 (fp32-equivalent)", "tf32": "single-pass TF32",
+                                  "bf16x3": "error-compensated BF16x3 (hi/lo split operands, fp32 accumulate) for forward and data-gradient GEMMs, 3xTF32 weight-gradient GEMMs"}[precision],
                    "parallelism": f"dp{ws}", "global_batch": B * ws,
                    "timing": "CUDA events per step; 256 MiB L2 flush (untimed) between steps; " + ("CUDA graph replay" if graph is not None else "eager launches")
                              + "; e2e: batch double-buffered from pinned host memory on a copy stream, every step's H2D + loss D2H inside the timed region"},

@@ -527,11 +527,13 @@ int mdb_attention_forward_f32(const float* q, const float* k, const float* v, co
     if (rc) return rc;
     dim3 grid((Lq + BR - 1) / BR, H, B);
     constexpr int kFwdSmem = 4 * BC * LDS * 4 + 2 * STG * 4 + BC;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};                 // the attribute is per (function, device): several devices per process
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (!attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem);
         if (e != cudaSuccess) return (int)e;
-        attr_set = true;
+        attr_set[dev] = true;
     }
     attn_fwd_kernel<<<grid, ATT_THREADS, kFwdSmem, static_cast<cudaStream_t>(stream)>>>(p);
     return (int)cudaGetLastError();

@@ -5,12 +5,13 @@
 
 extern "C" {
 
-int mdb_abi_version(void) { return 1; }
+int mdb_abi_version(void) { return 2; }
 
 const char* mdb_error_string(int code) {
     if (code == 0) return "ok";
     if (code == MDB_EINVAL) return "monodetr_b200: invalid argument (size, null or misaligned pointer)";
     if (code == MDB_EUNSUPPORTED) return "monodetr_b200: shape not supported by the sm_100a kernels";
+    if (code == MDB_EWORKSPACE) return "monodetr_b200: scratch workspace missing or too small (mdb_set_workspace)";
     if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
     return "monodetr_b200: unknown error";
 }

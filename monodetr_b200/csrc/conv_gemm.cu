@@ -76,10 +76,24 @@ struct TcParams {
 //                   lo = x - trunc_tf32(x) of both tiles next to the raw tiles; the MMA warp then issues
 //                   A*B + A_lo*B + A*B_lo (the tensor core truncates the raw fp32 bits itself) = ~fp32 accuracy.
 //                   With TA (default) the A tile and its lo part go to TENSOR MEMORY instead (see kStageBytes below).
-template <int BN, int STAGES, int MODE /*0 fprop/dgrad, 1 wgrad*/, bool B_MN, bool SPLIT, bool TA = false>
+//   BF (bf16x3)     error-compensated BF16: the B operand arrives PRE-SPLIT from global memory -- packed weights
+//                   [tap][n][k-block][hi 32 | lo 32] bf16, one 128-byte swizzle row per (n, k-block), written once per step
+//                   by pack_gemm_weights_bf16x3 -- and the splitter warps turn each landed fp32 A row into packed bf16
+//                   hi / lo pairs in TENSOR MEMORY.  Per k-block the tensor core issues A_hi*B_hi + A_lo*B_hi + A_hi*B_lo
+//                   as kind::f16 MMAs (K = 16): the same three products as 3xTF32 at twice the tensor rate, half the
+//                   operand bytes and no shared-memory rewrite of B (the 3xTF32 main loop is shared-memory-bandwidth
+//                   bound, profiles/r01_conv_gemm_tmemA_k256_ncu.txt).  Dropped terms are O(2^-17) per product.
+//   TS (TMA store)  epilogue variant for outputs without residual / mask / atomics: TMEM -> registers (+ bias, ReLU) ->
+//                   the warp's XOR-swizzled smem patch, which IS the SWIZZLE_128B image of a 32-row x 32-column box, ->
+//                   one cp.async.bulk.tensor store per chunk (double-buffered patches).  The per-row address arithmetic, the
+//                   patch read-back and the 8 predicated STG.128 per chunk of the register path -- which made every GEMM
+//                   with K <= 512 epilogue-bound (~1750 cycles per 32x32 chunk, gpurun r2 timelines) -- disappear; edge
+//                   clipping is done by the TMA unit.
+template <int BN, int STAGES, int MODE /*0 fprop/dgrad, 1 wgrad*/, bool B_MN, bool SPLIT, bool TA = false, bool BF = false,
+          bool TS = false>
 __global__ void __launch_bounds__(SPLIT ? 192 + 32 * kEpiWarps : 192)
 tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                    const __grid_constant__ TcParams p) {
+                    const __grid_constant__ CUtensorMap mapO, const __grid_constant__ TcParams p) {
     constexpr bool A_MN = (MODE == 1);
     constexpr int kTileBBytes = BN * 128;
     constexpr int kRawBytes = kTileABytes + kTileBBytes;          // what TMA delivers per stage
@@ -90,8 +104,10 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // 128 B/clk, profiles/r01_conv_gemm_timeline_k256.txt) -- and frees the smem for one more pipeline stage.
     // TMEM columns: [0, 2*BN) two accumulators, then per stage 32 columns raw A + 32 columns lo A.
     static_assert(!TA || SPLIT, "TMEM-resident A: 3xTF32 kernels only");
-    static_assert(!TA || 2 * BN + 64 * STAGES <= 512, "TMEM budget");
-    constexpr int kStageBytes = TA ? kTileABytes + 2 * kTileBBytes : (SPLIT ? 2 * kRawBytes : kRawBytes);  // + the lo tiles
+    static_assert(!BF || (TA && MODE == 0 && !B_MN), "bf16x3: fprop / dgrad with K-major pre-split weights");
+    constexpr int kAColsPerStage = BF ? 32 : 64;                  // TMEM columns of one stage's A operand (hi + lo)
+    static_assert(!TA || 2 * BN + kAColsPerStage * STAGES <= 512, "TMEM budget");
+    constexpr int kStageBytes = BF ? kRawBytes : (TA ? kTileABytes + 2 * kTileBBytes : (SPLIT ? 2 * kRawBytes : kRawBytes));  // + the lo tiles
     constexpr int kBLoOff = TA ? kTileBBytes : kRawBytes;          // B lo relative to B raw
     constexpr int kTmemCols = TA ? 512 : 2 * BN;
     constexpr int kEpiWarp0 = SPLIT ? 6 : 2;                        // first epilogue warp
@@ -102,8 +118,10 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // shared address space and emit GENERIC ld/st for every smem access of the splitter and the epilogue (measured:
     // ~2000 cycles per 32-column epilogue chunk).  The kernel has no static smem, so the dynamic window starts at the
     // CTA's (1024-byte aligned) shared base; the assumption is checked once below.
+    static_assert(!TS || MODE == 0, "TMA-store epilogue: fprop / dgrad");
+    constexpr int kTsPatchBytes = TS ? 2 * (SPLIT ? kEpiWarps : 4) * kPatchBytes : 0;   // double-buffered, 1024-byte aligned
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes + kTsPatchBytes);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* split_bar = empty_bar + STAGES;                     // splitter warps -> MMA (SPLIT only)
     uint64_t* tmem_full = split_bar + STAGES;                     // [2]
@@ -150,6 +168,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         if (smem_u32(smem) & 1023u) __trap();                     // SWIZZLE_128B tiles need 1024-byte aligned stages
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapB);
+        if constexpr (TS) tma_prefetch_desc(&mapO);
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -187,7 +206,9 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         const int cb = kit - tap * p.cblocks;
                         tma_load_4d(a_dst, &mapA, &full_bar[s], cb * BK, t.x0 * p.in_sx + p.tap_dx[tap],
                                     t.y0 * p.in_sy + p.tap_dy[tap], t.img);
-                        if constexpr (!B_MN) {
+                        if constexpr (BF) {   // bf16 map: one 128-byte row = [hi 32 | lo 32] of k-block cb
+                            tma_load_3d(b_dst, &mapB, &full_bar[s], cb * 64, t.n0, p.tap_w[tap]);
+                        } else if constexpr (!B_MN) {
                             tma_load_3d(b_dst, &mapB, &full_bar[s], cb * BK, t.n0, p.tap_w[tap]);
                         } else {
 #pragma unroll
@@ -215,7 +236,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     } else if (warp == 1) {
         // ================================ MMA issuer ==============================================
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_tf32(BM, BN, A_MN && !TA, B_MN);   // A from TMEM is always lane = m, column = k
+            constexpr uint32_t idesc = BF ? make_idesc_bf16(BM, BN) : make_idesc_tf32(BM, BN, A_MN && !TA, B_MN);   // A from TMEM is always lane = m, column = k
             constexpr uint64_t kDescHiA = (A_MN ? make_smem_desc(0, kChunkBytes, 512, 1) : make_smem_desc(0, 16, 1024, 2)) & 0xFFFFFFFF00000000ull;
             constexpr uint64_t kDescHiB = (B_MN ? make_smem_desc(0, kChunkBytes, 512, 1) : make_smem_desc(0, 16, 1024, 2)) & 0xFFFFFFFF00000000ull;
             constexpr uint32_t kDescLoA = (uint32_t)((A_MN ? make_smem_desc(0, kChunkBytes, 512, 1) : make_smem_desc(0, 16, 1024, 2)) & 0xFFFF0000ull);
@@ -244,6 +265,19 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     // 4-row groups 512 B apart (SBO); 32-wide MN chunks 4096 B apart (LBO).
                     const uint32_t a_addr = smem_base_u32 + s * kStageBytes;
                     const uint32_t b_addr = a_addr + kTileABytes;
+                    if constexpr (BF) {
+                        // bf16x3: k-step = 16 bf16 = 8 TMEM columns of A (two per 32-bit column) / 32 bytes of a B row;
+                        // A hi at columns [0,16) of the stage, lo at [16,32); B hi at bytes [0,64) of the row, lo at [64,128).
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const uint32_t ta = tmem_base + 2 * BN + s * kAColsPerStage + ks * 8;
+                            const uint64_t bhi = kDescHiB | (uint64_t)(kDescLoB | (((b_addr + ks * 32) >> 4) & 0x3FFFu));
+                            const uint64_t blo = kDescHiB | (uint64_t)(kDescLoB | (((b_addr + 64 + ks * 32) >> 4) & 0x3FFFu));
+                            umma_bf16_ta(tacc, ta, bhi, idesc, (it > 0) || (ks > 0));
+                            umma_bf16_ta(tacc, ta + 16, bhi, idesc, true);
+                            umma_bf16_ta(tacc, ta, blo, idesc, true);
+                        }
+                    } else {
 #pragma unroll
                     for (int k = 0; k < BK / 8; ++k) {
                         const uint32_t ao = A_MN ? k * 1024 : k * 32, bo = B_MN ? k * 1024 : k * 32;
@@ -265,6 +299,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                             }
                         }
                     }
+                    }
                     umma_commit(&empty_bar[s]);                   // frees the smem stage when these MMAs retire
                 }
                 umma_commit(&tmem_full[slot]);                    // accumulator complete
@@ -283,7 +318,26 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 const int s = git % STAGES;
                 const uint32_t ph = (git / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
-                if constexpr (TA) {
+                if constexpr (BF) {
+                    // This thread owns tile row (warp % 4) * 32 + lane = its TMEM lane: 32 fp32 -> 16 packed bf16x2 hi words
+                    // (element 2j in the low half) + 16 lo words, lo = bf16(x - float(hi)) (the subtraction is exact).
+                    const int row = (warp & 3) * 32 + lane;
+                    const uint8_t* arow = smem + s * kStageBytes + row * 128;
+                    uint32_t w[32];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 r = *reinterpret_cast<const uint4*>(arow + ((c ^ (row & 7)) << 4));
+                        const float x0 = __uint_as_float(r.x), x1 = __uint_as_float(r.y), x2 = __uint_as_float(r.z), x3 = __uint_as_float(r.w);
+                        const uint32_t h01 = pack_bf16x2(x0, x1), h23 = pack_bf16x2(x2, x3);
+                        w[2 * c] = h01;
+                        w[2 * c + 1] = h23;
+                        w[16 + 2 * c] = pack_bf16x2(x0 - __uint_as_float(h01 << 16), x1 - __uint_as_float(h01 & 0xFFFF0000u));
+                        w[16 + 2 * c + 1] = pack_bf16x2(x2 - __uint_as_float(h23 << 16), x3 - __uint_as_float(h23 & 0xFFFF0000u));
+                    }
+                    tmem_st_32x32(tmem_base + 2 * BN + s * kAColsPerStage + ((uint32_t)((warp & 3) * 32) << 16), w);
+                    tmem_st_wait();
+                    tc_fence_before();             // order the TMEM stores before the MMA thread's reads (pairs with its fence::after)
+                } else if constexpr (TA) {
                     // A: this thread owns tile row (warp % 4) * 32 + lane = its TMEM lane.  K-major SWIZZLE_128B smem: row r
                     // is 128 bytes, 16-byte chunk c sits at c ^ (r & 7) (conflict-free: 8 lanes hit 8 different chunks).
                     const int row = (warp & 3) * 32 + lane;
@@ -366,6 +420,75 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         // transposed through a private XOR-swizzled smem patch: afterwards 8 lanes x float4 cover one row's 128 bytes and
         // a warp instruction moves 4 full lines -- residual / mask reads use the same coalesced pattern.
         const int q = warp & 3;                // TMEM lane quarter this warp may access
+        if constexpr (TS) {
+            // ---- TMA-store epilogue ----------------------------------------------------------------------------------
+            uint8_t* patches = smem + STAGES * kStageBytes + (warp - kEpiWarp0) * 2 * kPatchBytes;
+            const int chunk0 = ((warp - kEpiWarp0) >> 2) * 32;
+            // first row of this warp's 32-row slice inside the tile (tw, th, tb are powers of two with product 128)
+            const int r0 = q * 32;
+            const int lx0 = r0 % p.tw, lyt0 = r0 / p.tw, ib0 = lyt0 / p.th, ly0 = lyt0 - ib0 * p.th;
+            int lt = 0, nbuf = 0;
+            for (int tix = blockIdx.x; tix < p.total_tiles; tix += gridDim.x) {
+                const Tile t = decode(tix);
+                const int slot = lt & 1;
+                const bool dbg = p.dbg && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0 && lt < 12;
+                if (dbg) p.dbg[lt * 16 + 0] = clock64();
+                if (t.iters > 0) {
+                    mbar_wait(&tmem_full[slot], (lt >> 1) & 1);
+                    tc_fence_after();
+                }
+                if (dbg) p.dbg[lt * 16 + 1] = clock64();
+                const uint32_t taddr_row = tmem_base + slot * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+                for (int c0 = chunk0; c0 < BN; c0 += 32 * (EPI / 4)) {
+                    if (t.n0 + c0 >= p.No) break;  // uniform across the warp
+                    uint8_t* patch = patches + (nbuf & 1) * kPatchBytes;
+                    ++nbuf;
+                    // the bulk store issued from this buffer two chunks ago must have finished reading it
+                    if (lane == 0) tma_store_wait_read<1>();
+                    __syncwarp();
+                    uint32_t r[32];
+                    if (t.iters > 0) {
+                        tmem_ld_32x32(taddr_row + c0, r);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = 0u;
+                    }
+                    float4 b4[8];
+                    if (p.bias) {                  // per-column bias: the same 128 bytes for every lane (broadcast loads)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            b4[j] = (t.n0 + c0 + 4 * j < p.No) ? __ldg(reinterpret_cast<const float4*>(p.bias + t.n0 + c0) + j)
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (t.iters > 0) tmem_ld_wait();
+                    if (dbg && c0 < 128) p.dbg[lt * 16 + 2 + (c0 >> 5) * 3] = clock64();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                               __uint_as_float(r[4 * j + 3]));
+                        if (p.bias) { v.x += b4[j].x; v.y += b4[j].y; v.z += b4[j].z; v.w += b4[j].w; }
+                        if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        *reinterpret_cast<float4*>(patch + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
+                    }
+                    fence_proxy_async_smem();      // generic-proxy writes -> visible to the TMA unit's async-proxy reads
+                    __syncwarp();
+                    if (dbg && c0 < 128) p.dbg[lt * 16 + 3 + (c0 >> 5) * 3] = clock64();
+                    if (lane == 0) {
+                        tma_store_4d(&mapO, patch, t.n0 + c0, t.x0 + lx0, t.y0 + ly0, t.img + ib0);
+                        tma_store_commit();
+                    }
+                    if (dbg && c0 < 128) p.dbg[lt * 16 + 4 + (c0 >> 5) * 3] = clock64();
+                }
+                if (t.iters > 0) {
+                    tc_fence_before();             // TMEM reads of this warp are done: hand the accumulator back
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+                    ++lt;
+                }
+            }
+            if (lane == 0) tma_store_wait_all();   // every bulk store of this warp has been written out before the CTA exits
+        } else {
         float* patch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256) + (warp - kEpiWarp0) * (32 * 32);
         const int chunk0 = ((warp - kEpiWarp0) >> 2) * 32;       // EPI == 8: warps 4..7 take the odd 32-column chunks
         const int r4 = lane >> 3, c4 = lane & 7;
@@ -517,6 +640,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 ++lt;
             }
         }
+        }   // !TS
     }
     tc_fence_before();
     __syncthreads();
@@ -547,8 +671,8 @@ EncodeTiledFn get_encode() {
 }
 
 // dims/strides innermost first; strides in ELEMENTS for dims 1..rank-1 (dim 0 is contiguous).
-int make_map(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-             const uint32_t* box, const uint32_t* estr, bool mn_major = false) {
+int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+             const uint32_t* box, const uint32_t* estr, bool mn_major = false, bool bf16 = false) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return MDB_EUNSUPPORTED;
     cuuint64_t gdim[5], gstr[4];
@@ -559,11 +683,12 @@ int make_map(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, 
         es[i] = estr ? estr[i] : 1;
     }
     for (int i = 1; i < rank; ++i) {
-        gstr[i - 1] = strides_elems[i] * sizeof(float);
+        gstr[i - 1] = strides_elems[i] * (bf16 ? 2 : sizeof(float));
         if (gstr[i - 1] % 16) return MDB_EINVAL;
     }
     if (reinterpret_cast<uintptr_t>(base) % 16) return MDB_EINVAL;
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr, bx, es,
+    CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                     const_cast<void*>(base), gdim, gstr, bx, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE,
                      mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -572,31 +697,54 @@ int make_map(CUtensorMap* m, const float* base, int rank, const uint64_t* dims, 
 }
 
 long long* g_dbg = nullptr;   // see mdb_debug_set_timeline
-int g_precision = 1;   // 0 = single-pass TF32 (operands rounded to nearest), 1 = error-compensated 3xTF32 (default)
+// Arithmetic mode: a process-wide numerical setting (like torch.backends.cuda.matmul.allow_tf32), not per-device state.
+// 0 = single-pass TF32 (operands rounded to nearest), 1 = error-compensated 3xTF32, 2 = error-compensated BF16x3 for
+// fprop / dgrad with pre-split weights (wgrad stays 3xTF32).
+int g_precision = 1;
+
+// Everything that belongs to ONE device lives here, keyed by cudaGetDevice() (several devices per process: nn.DataParallel,
+// tools/train_val.py:50-55): SM count, the split-K scratch registered by the caller, and (in launch_tc) the per-kernel
+// max-dynamic-smem attribute, which is a per-device property of a function.
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+    int sms = 0;
+    float* ws = nullptr;         // split-K scratch: owned by the CALLER (mdb_set_workspace), never freed / reallocated here
+    size_t ws_bytes = 0;
+};
+DeviceState g_dev[kMaxDevices];
+
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+    return dev;
+}
 
 int num_sms_tc() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
+    DeviceState& d = g_dev[current_device()];
+    if (d.sms == 0) {
+        int dev = 0, sms = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+        d.sms = sms;
     }
-    return sms;
+    return d.sms;
 }
 
 // `grid` carries the logical tile counts (x = column tiles, y = row tiles, z = split-K slices); the kernel is
 // launched persistent with min(total_tiles, SMs * resident CTAs) CTAs.
-template <int BN, int STAGES, int MODE, bool B_MN, bool SPLIT, bool TA = false>
-int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, dim3 grid, cudaStream_t stream) {
-    constexpr int stage = TA ? kTileABytes + 2 * BN * 128 : (SPLIT ? 2 : 1) * (kTileABytes + BN * 128);
-    constexpr int smem = STAGES * stage + 1024 /*align slack*/ + 256 /*barriers*/ + (SPLIT ? kEpiWarps : 4) * kPatchBytes;
+template <int BN, int STAGES, int MODE, bool B_MN, bool SPLIT, bool TA = false, bool BF = false, bool TS = false>
+int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, dim3 grid, cudaStream_t stream, const CUtensorMap* o = nullptr) {
+    constexpr int stage = BF ? kTileABytes + BN * 128 : (TA ? kTileABytes + 2 * BN * 128 : (SPLIT ? 2 : 1) * (kTileABytes + BN * 128));
+    constexpr int smem = STAGES * stage + 1024 /*align slack*/ + 256 /*barriers*/ + (TS ? 2 : 1) * (SPLIT ? kEpiWarps : 4) * kPatchBytes;
     static_assert(smem <= 227 * 1024, "dynamic shared memory budget");
     constexpr int threads = SPLIT ? 192 + 32 * kEpiWarps : 192;
-    static bool configured = false;
-    auto kern = tc_conv_gemm_kernel<BN, STAGES, MODE, B_MN, SPLIT, TA>;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};                     // the attribute is per (function, device)
+    auto kern = tc_conv_gemm_kernel<BN, STAGES, MODE, B_MN, SPLIT, TA, BF, TS>;
+    if (TS && !o) return MDB_EINVAL;
+    const int dev = current_device();
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured[dev] = true;
     }
     p.n_tiles_n = (int)grid.x;
     p.n_tiles_m = (int)grid.y;
@@ -605,7 +753,7 @@ int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, dim3 grid,
     int ctas = num_sms_tc() * resident;
     if (ctas > p.total_tiles) ctas = p.total_tiles;
     if (ctas < 1) return 0;
-    kern<<<ctas, threads, smem, stream>>>(a, b, p);
+    kern<<<ctas, threads, smem, stream>>>(a, b, o ? *o : a, p);
     return (int)cudaGetLastError();
 }
 
@@ -622,18 +770,13 @@ __global__ void splitk_reduce_kernel(const float4* __restrict__ ws, const float4
     }
 }
 
-// Scratch for the split-K partial tiles: grown outside stream capture only (the eager warm-up steps size it).
-float* g_splitk_ws = nullptr;
-size_t g_splitk_ws_bytes = 0;
+// Scratch for the split-K partial tiles.  The library never allocates: the caller registers a buffer for the current
+// device (mdb_set_workspace; the Python side takes it from torch's caching allocator, which is CUDA-graph and
+// multi-stream aware) after asking mdb_conv2d_forward_workspace_bytes.  Too small / missing -> MDB_EWORKSPACE.
 int splitk_workspace(size_t bytes, float** out) {
-    if (bytes > g_splitk_ws_bytes) {
-        if (g_splitk_ws) cudaFree(g_splitk_ws);
-        g_splitk_ws = nullptr; g_splitk_ws_bytes = 0;
-        cudaError_t e = cudaMalloc(&g_splitk_ws, bytes);
-        if (e != cudaSuccess) return (int)e;
-        g_splitk_ws_bytes = bytes;
-    }
-    *out = g_splitk_ws;
+    DeviceState& d = g_dev[current_device()];
+    if (bytes > d.ws_bytes || !d.ws) return MDB_EWORKSPACE;
+    *out = d.ws;
     return 0;
 }
 
@@ -664,6 +807,22 @@ void pick_tile3(int W, int H, int B, int n_pix, int* tw, int* th, int* tb) {
         }
 }
 
+// Output tensor map of the TMA-store epilogue (TS kernels): out as (No, W, H, images) with one epilogue warp's 32-row slice
+// of the tw x th x tb tile as the box.  Returns false when the register epilogue has to be used instead.
+bool make_out_map(CUtensorMap* mo, const TcParams& p) {
+    static const bool enabled = getenv("MDB_NO_TMA_STORE") == nullptr;            // A/B switch (profiling)
+    if (!enabled || p.residual || p.relu_mask || p.atomic_out || p.kb_per_slice > 0 || p.round_out) return false;
+    if (p.out_sx != 1 || p.out_sy != 1 || p.out_ox != 0 || p.out_oy != 0 || (p.ldo & 3) || p.No != p.ldo) return false;
+    if ((reinterpret_cast<uintptr_t>(p.out) & 15u) || (p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15u))) return false;
+    const int bw = p.tw < 32 ? p.tw : 32;
+    const int bh = p.th < 32 / bw ? p.th : 32 / bw;
+    const int bb = 32 / (bw * bh);
+    uint64_t dims[4] = {(uint64_t)p.No, (uint64_t)p.out_W, (uint64_t)p.out_H, (uint64_t)p.n_img};
+    uint64_t str[4] = {1, (uint64_t)p.ldo, (uint64_t)p.out_W * p.ldo, (uint64_t)p.out_H * p.out_W * p.ldo};
+    uint32_t box[4] = {32, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
+    return make_map(mo, p.out, 4, dims, str, box, nullptr) == 0;
+}
+
 struct ConvGeom {
     int B, H, W, Cin, Cout, kh, kw, stride, pad, Ho, Wo;
 };
@@ -684,21 +843,37 @@ extern "C" {
 void mdb_debug_set_timeline(long long* device_buf) { g_dbg = device_buf; }
 
 int mdb_set_precision(int mode) {
-    if (mode != 0 && mode != 1) return MDB_EINVAL;
+    if (mode < 0 || mode > 2) return MDB_EINVAL;
     g_precision = mode;
     return 0;
 }
 int mdb_get_precision(void) { return g_precision; }
 
-// y[B,Ho,Wo,Cout] = act( conv(x[B,H,W,Cin], w_packed[kh*kw][Cout][Cin]) + bias + residual )
-int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
-                           int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int flags,
-                           void* stream_) {
+}  // extern "C"
+
+namespace {
+
+// Split-K decision of the forward (shared by the launcher and mdb_conv2d_forward_workspace_bytes): a handful of tiles
+// with a very long reduction (the 3x3 stride-2 2048->256 neck convolution: 16-32 tiles x 576 k-blocks kept a fifth of
+// the SMs busy for 0.3 ms).  Returns the number of slices (0 = no split-K).
+int forward_splitk_slices(int precision, int tiles, int kblocks, int bn, bool plain_epilogue, int Cout, long long out_elems) {
+    const int kb_per_slice = 32;
+    if (precision == 0 || bn != 128 || tiles * 2 > num_sms_tc() || kblocks < 256 || !plain_epilogue || Cout % 4) return 0;
+    const int slices = (kblocks + kb_per_slice - 1) / kb_per_slice;
+    return (out_elems * slices < (1ll << 31)) ? slices : 0;
+}
+
+// y[B,Ho,Wo,Cout] = act( conv(x[B,H,W,Cin], w) + bias + residual );  w = fp32 packed [kh*kw][Cout][Cin] (bf == false)
+// or the pre-split bf16 form [kh*kw][Cout][ceil(Cin/32)][hi 32 | lo 32] (bf == true, precision mode 2).
+int conv_forward_impl(const float* x, const void* w_packed, bool bf, const float* bias, const float* residual, float* y,
+                      int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int flags,
+                      void* stream_, size_t* query_ws = nullptr /* non-null: only report the scratch bytes this call needs */) {
+    const int precision = bf ? 2 : (g_precision == 2 ? 1 : g_precision);   // fp32 weights in bf16x3 mode: 3xTF32
     ConvGeom g{B, H, W, Cin, Cout, kh, kw, stride, pad, (H + 2 * pad - kh) / stride + 1, (W + 2 * pad - kw) / stride + 1};
     int rc = check_geom(g, true);
     if (rc) return rc;
-    if (!x || !w_packed || !y) return MDB_EINVAL;
-    if ((unsigned long long)B * g.Ho * g.Wo * Cout >= (1ull << 32)) return MDB_EUNSUPPORTED;   // the epilogue indexes with 32 bits
+    if (!query_ws && (!x || !w_packed || !y)) return MDB_EINVAL;
+    if ((unsigned long long)B * g.Ho * g.Wo * Cout >= (1ull << 31)) return MDB_EUNSUPPORTED;   // the epilogue indexes with (signed) 32 bits
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (kh == 1 && stride == 1 && pad == 0) {     // pointwise: the batch of images is one long row of pixels (no tile waste)
         W = B * H * W; H = 1; B = 1;
@@ -722,8 +897,26 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
             p.tap_dy[t] = ky - pad; p.tap_dx[t] = kx - pad; p.tap_w[t] = t;
         }
     p.wg_taps = 1; p.wg_kw = 1;
-    p.No = Cout; p.ldo = Cout; p.relu = flags & 1; p.round_out = (g_precision == 0) ? ((flags >> 1) & 1) : 0; p.atomic_out = 0;
+    p.No = Cout; p.ldo = Cout; p.relu = flags & 1; p.round_out = (precision == 0) ? ((flags >> 1) & 1) : 0; p.atomic_out = 0;
     p.bias = bias; p.residual = residual; p.relu_mask = nullptr; p.rowscale = nullptr; p.out = y; p.dbg = g_dbg;
+
+    // 128x256 3xTF32 tiles are only used when the TMEM-A variant is switched off (it is faster than them everywhere measured)
+    static const bool wide_split = getenv("MDB_NO_TMEM_A") != nullptr && getenv("MDB_NO_WIDE_SPLIT") == nullptr;
+    static const bool tmem_a = getenv("MDB_NO_TMEM_A") == nullptr;            // A/B switch (profiling)
+    // 3xTF32: a 128x256 tile needs 96 KB per stage -> only 2 stages fit, which cannot hide DRAM latency; it pays off
+    // only when the A operand is re-read from L2 (multi-tap convolutions), measured +6 % on 3x3 256->256.
+    const bool wide = (precision == 0 || (precision == 1 && wide_split && kh * kw > 1)) && (Cout % 256 == 0) &&
+                      ((long long)n_groups * p.tiles_x * p.tiles_y * (Cout / 256) >= 100);
+    const int bn = wide ? 256 : (Cout <= 64 ? 64 : 128);
+    dim3 grid((Cout + bn - 1) / bn, n_groups * p.tiles_x * p.tiles_y, 1);
+    const long long out_elems = (long long)B * g.Ho * g.Wo * Cout;
+    const int slices = (tmem_a && (reinterpret_cast<uintptr_t>(bias) & 15u) == 0)
+                           ? forward_splitk_slices(precision, (int)(grid.x * grid.y), p.ntaps * p.cblocks, bn, !residual && !p.relu, Cout, out_elems)
+                           : 0;
+    if (query_ws) {
+        *query_ws = sizeof(float) * (size_t)out_elems * slices;
+        return 0;
+    }
 
     CUtensorMap ma, mb;
     {   // A: x as (C, W, H, B), box (32, tw*s, th*s, 1), element strides (1, s, s, 1)
@@ -735,71 +928,71 @@ int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* b
         rc = make_map(&ma, x, 4, dims, str, box, es);
         if (rc) return rc;
     }
-    // 128x256 3xTF32 tiles are only used when the TMEM-A variant is switched off (it is faster than them everywhere measured)
-    static const bool wide_split = getenv("MDB_NO_TMEM_A") != nullptr && getenv("MDB_NO_WIDE_SPLIT") == nullptr;
-    // 3xTF32: a 128x256 tile needs 96 KB per stage -> only 2 stages fit, which cannot hide DRAM latency; it pays off
-    // only when the A operand is re-read from L2 (multi-tap convolutions), measured +6 % on 3x3 256->256.
-    const bool wide = (g_precision == 0 || (wide_split && kh * kw > 1)) && (Cout % 256 == 0) &&
-                      ((long long)n_groups * p.tiles_x * p.tiles_y * (Cout / 256) >= 100);
-    const int bn = wide ? 256 : (Cout <= 64 ? 64 : 128);
-    {   // B: packed weights as (Cin, Cout, taps), box (32, BN, 1)
+    if (bf) {   // B: pre-split bf16 weights as (64 * k-blocks, Cout, taps), box (64 = one [hi 32 | lo 32] row, BN, 1)
+        const uint64_t kb = (uint64_t)p.cblocks;
+        uint64_t dims[3] = {64 * kb, (uint64_t)Cout, (uint64_t)(kh * kw)};
+        uint64_t str[3] = {1, 64 * kb, (uint64_t)Cout * 64 * kb};
+        uint32_t box[3] = {64, (uint32_t)bn, 1};
+        rc = make_map(&mb, w_packed, 3, dims, str, box, nullptr, false, true);
+        if (rc) return rc;
+    } else {   // B: packed weights as (Cin, Cout, taps), box (32, BN, 1)
         uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
         uint64_t str[3] = {1, (uint64_t)Cin, (uint64_t)Cout * Cin};
         uint32_t box[3] = {BK, (uint32_t)bn, 1};
         rc = make_map(&mb, w_packed, 3, dims, str, box, nullptr);
         if (rc) return rc;
     }
-    dim3 grid((Cout + bn - 1) / bn, n_groups * p.tiles_x * p.tiles_y, 1);
-    static const bool tmem_a = getenv("MDB_NO_TMEM_A") == nullptr;            // A/B switch (profiling)
-    // Split-K for a handful of tiles with a very long reduction (the 3x3 stride-2 2048->256 neck convolution: 16-32 tiles x
-    // 576 k-blocks kept a fifth of the SMs busy for 0.3 ms).  Slices write partial tiles to a scratch buffer and a second
-    // kernel adds them in a fixed order (+ bias): bit-reproducible, unlike atomic accumulation.
+    // Split-K (see forward_splitk_slices): slices write partial tiles to the caller's scratch buffer and a second kernel adds
+    // them in a fixed order (+ bias): bit-reproducible, unlike atomic accumulation.  The slice length is fixed and only
+    // reductions >= 256 k-blocks take this path, so the summation order does not depend on the batch size.
     {
-        const int tiles = (int)(grid.x * grid.y), kblocks = p.ntaps * p.cblocks, sms = num_sms_tc();
-        const long long out_elems = (long long)B * g.Ho * g.Wo * Cout;
-        if (g_precision == 1 && tmem_a && bn == 128 && tiles * 2 <= sms && kblocks >= 256 && !residual && !p.relu && Cout % 4 == 0 &&
-            (reinterpret_cast<uintptr_t>(bias) & 15u) == 0) {
-            // fixed slice length, and only reductions so long (>= 256 k-blocks) that every sane batch size takes this path:
-            // the summation order must not depend on the batch size (same image -> same bits for B = 1 or 8)
+        if (slices > 0) {
+            float* ws = nullptr;
+            rc = splitk_workspace(sizeof(float) * (size_t)out_elems * slices, &ws);
+            if (rc) return rc;
             p.kb_per_slice = 32;
-            const int slices = (kblocks + p.kb_per_slice - 1) / p.kb_per_slice;
-            if (out_elems * slices < (1ll << 31)) {
-                float* ws = nullptr;
-                rc = splitk_workspace(sizeof(float) * (size_t)out_elems * slices, &ws);
-                if (rc) return rc;
-                p.slice_stride = (int)out_elems;
-                p.out = ws; p.bias = nullptr;
-                grid.z = slices;
-                rc = launch_tc<128, 4, 0, false, true, true>(ma, mb, p, grid, stream);
-                if (rc) return rc;
-                const long long n4 = out_elems / 4;
-                const int blocks = (int)((n4 + 255) / 256 > 1184 ? 1184 : (n4 + 255) / 256);
-                splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(ws), reinterpret_cast<const float4*>(bias),
-                                                                 reinterpret_cast<float4*>(y), n4, Cout / 4, slices, n4);
-                return (int)cudaGetLastError();
-            }
-            p.kb_per_slice = 0;
+            p.slice_stride = (int)out_elems;
+            p.out = ws; p.bias = nullptr;
+            grid.z = slices;
+            rc = bf ? launch_tc<128, 6, 0, false, true, true, true>(ma, mb, p, grid, stream)
+                    : launch_tc<128, 4, 0, false, true, true>(ma, mb, p, grid, stream);
+            if (rc) return rc;
+            const long long n4 = out_elems / 4;
+            const int blocks = (int)((n4 + 255) / 256 > 1184 ? 1184 : (n4 + 255) / 256);
+            splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(ws), reinterpret_cast<const float4*>(bias),
+                                                             reinterpret_cast<float4*>(y), n4, Cout / 4, slices, n4);
+            return (int)cudaGetLastError();
         }
     }
-    if (bn == 64) return (g_precision == 1) ? (tmem_a ? launch_tc<64, 6, 0, false, true, true>(ma, mb, p, grid, stream)
-                                                      : launch_tc<64, 4, 0, false, true>(ma, mb, p, grid, stream))
-                                            : launch_tc<64, 6, 0, false, false>(ma, mb, p, grid, stream);
-    if (g_precision == 1 && wide) return launch_tc<256, 2, 0, false, true>(ma, mb, p, grid, stream);
-    if (g_precision == 1) return tmem_a ? launch_tc<128, 4, 0, false, true, true>(ma, mb, p, grid, stream)
-                                        : launch_tc<128, 3, 0, false, true>(ma, mb, p, grid, stream);
+    if (bf) {
+        CUtensorMap mo;
+        if (make_out_map(&mo, p))
+            return bn == 64 ? launch_tc<64, 8, 0, false, true, true, true, true>(ma, mb, p, grid, stream, &mo)
+                            : launch_tc<128, 6, 0, false, true, true, true, true>(ma, mb, p, grid, stream, &mo);
+        return bn == 64 ? launch_tc<64, 8, 0, false, true, true, true>(ma, mb, p, grid, stream)
+                        : launch_tc<128, 6, 0, false, true, true, true>(ma, mb, p, grid, stream);
+    }
+    if (bn == 64) return (precision == 1) ? (tmem_a ? launch_tc<64, 6, 0, false, true, true>(ma, mb, p, grid, stream)
+                                                    : launch_tc<64, 4, 0, false, true>(ma, mb, p, grid, stream))
+                                          : launch_tc<64, 6, 0, false, false>(ma, mb, p, grid, stream);
+    if (precision == 1 && wide) return launch_tc<256, 2, 0, false, true>(ma, mb, p, grid, stream);
+    if (precision == 1) return tmem_a ? launch_tc<128, 4, 0, false, true, true>(ma, mb, p, grid, stream)
+                                      : launch_tc<128, 3, 0, false, true>(ma, mb, p, grid, stream);
     if (wide) return launch_tc<256, 4, 0, false, false>(ma, mb, p, grid, stream);
     return launch_tc<128, 5, 0, false, false>(ma, mb, p, grid, stream);
 }
 
-// dx[B,H,W,Cin] = (conv_transpose(dy[B,Ho,Wo,Cout], w_packed) + residual) * (relu_mask > 0)
-int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* residual, const float* relu_mask,
-                         float* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
-                         int flags, void* stream_) {
+// dx[B,H,W,Cin] = (conv_transpose(dy[B,Ho,Wo,Cout], w) + residual) * (relu_mask > 0);  w = fp32 packed [taps][Cout][Cin]
+// (read MN-major) or, bf == true, the pre-split TRANSPOSED bf16 form [taps][Cin][ceil(Cout/32)][hi 32 | lo 32] (K-major).
+int conv_dgrad_impl(const float* dy, const void* w_packed, bool bf, const float* residual, const float* relu_mask,
+                    float* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
+                    int flags, void* stream_) {
+    const int precision = bf ? 2 : (g_precision == 2 ? 1 : g_precision);
     ConvGeom g{B, H, W, Cin, Cout, kh, kw, stride, pad, (H + 2 * pad - kh) / stride + 1, (W + 2 * pad - kw) / stride + 1};
     int rc = check_geom(g);
     if (rc) return rc;
     if (!dy || !w_packed || !dx) return MDB_EINVAL;
-    if ((unsigned long long)B * H * W * Cin >= (1ull << 32)) return MDB_EUNSUPPORTED;           // the epilogue indexes with 32 bits
+    if ((unsigned long long)B * H * W * Cin >= (1ull << 31)) return MDB_EUNSUPPORTED;           // the epilogue indexes with (signed) 32 bits
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (kh == 1 && stride == 1 && pad == 0) {     // pointwise: one long row of pixels
         W = B * H * W; H = 1; B = 1;
@@ -837,7 +1030,7 @@ int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* re
             }
             p.ntaps = nt;
             p.wg_taps = 1; p.wg_kw = 1;
-            p.No = Cin; p.ldo = Cin; p.relu = 0; p.atomic_out = 0; p.round_out = (g_precision == 0) ? ((flags >> 1) & 1) : 0;
+            p.No = Cin; p.ldo = Cin; p.relu = 0; p.atomic_out = 0; p.round_out = (precision == 0) ? ((flags >> 1) & 1) : 0;
             p.bias = nullptr; p.residual = residual; p.relu_mask = relu_mask; p.rowscale = nullptr; p.out = dx;
             CUtensorMap ma, mb;
             {   // A: dy as (Cout, Wo, Ho, B), unit stride
@@ -847,24 +1040,77 @@ int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* re
                 rc = make_map(&ma, dy, 4, dims, str, box, nullptr);
                 if (rc) return rc;
             }
-            {   // B (MN-major): packed weights as (Cin, Cout, taps); box = 32 output columns (Cin) x 32 reduction rows (Cout)
+            const int bn = (bf && Cin <= 64) ? 64 : 128;
+            if (bf) {   // B (K-major): transposed pre-split weights as (64 * k-blocks, Cin, taps); box (64, BN, 1)
+                const uint64_t kb = (uint64_t)p.cblocks;
+                uint64_t dims[3] = {64 * kb, (uint64_t)Cin, (uint64_t)(kh * kw)};
+                uint64_t str[3] = {1, 64 * kb, (uint64_t)Cin * 64 * kb};
+                uint32_t box[3] = {64, (uint32_t)bn, 1};
+                rc = make_map(&mb, w_packed, 3, dims, str, box, nullptr, false, true);
+                if (rc) return rc;
+            } else {   // B (MN-major): packed weights as (Cin, Cout, taps); box = 32 output columns (Cin) x 32 reduction rows (Cout)
                 uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
                 uint64_t str[3] = {1, (uint64_t)Cin, (uint64_t)Cout * Cin};
                 uint32_t box[3] = {32, 32, 1};
                 rc = make_map(&mb, w_packed, 3, dims, str, box, nullptr, true);
                 if (rc) return rc;
             }
-            dim3 grid((Cin + 127) / 128, n_groups * p.tiles_x * p.tiles_y, 1);
+            dim3 grid((Cin + bn - 1) / bn, n_groups * p.tiles_x * p.tiles_y, 1);
             if (nt == 0) {   // no tap reaches this parity class (1x1 stride 2): result = (0 + residual) * mask
                 p.ntaps = 0;
             }
             static const bool tmem_a = getenv("MDB_NO_TMEM_A") == nullptr;
-            rc = (g_precision == 1) ? (tmem_a ? launch_tc<128, 4, 0, true, true, true>(ma, mb, p, grid, stream)
-                                              : launch_tc<128, 3, 0, true, true>(ma, mb, p, grid, stream))
-                                    : launch_tc<128, 5, 0, true, false>(ma, mb, p, grid, stream);
+            CUtensorMap mo;
+            if (bf && make_out_map(&mo, p))
+                rc = bn == 64 ? launch_tc<64, 8, 0, false, true, true, true, true>(ma, mb, p, grid, stream, &mo)
+                              : launch_tc<128, 6, 0, false, true, true, true, true>(ma, mb, p, grid, stream, &mo);
+            else if (bf) rc = bn == 64 ? launch_tc<64, 8, 0, false, true, true, true>(ma, mb, p, grid, stream)
+                                       : launch_tc<128, 6, 0, false, true, true, true>(ma, mb, p, grid, stream);
+            else rc = (precision == 1) ? (tmem_a ? launch_tc<128, 4, 0, true, true, true>(ma, mb, p, grid, stream)
+                                                 : launch_tc<128, 3, 0, true, true>(ma, mb, p, grid, stream))
+                                       : launch_tc<128, 5, 0, true, false>(ma, mb, p, grid, stream);
             if (rc) return rc;
         }
     return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mdb_conv2d_forward_f32(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
+                           int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int flags,
+                           void* stream) {
+    return conv_forward_impl(x, w_packed, false, bias, residual, y, B, H, W, Cin, Cout, kh, kw, stride, pad, flags, stream);
+}
+int mdb_conv2d_forward_bf16x3(const float* x, const void* w_split, const float* bias, const float* residual, float* y,
+                              int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int flags,
+                              void* stream) {
+    return conv_forward_impl(x, w_split, true, bias, residual, y, B, H, W, Cin, Cout, kh, kw, stride, pad, flags, stream);
+}
+long long mdb_conv2d_forward_workspace_bytes(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
+                                             int flags, int has_residual, int split_weights) {
+    size_t bytes = 0;
+    const float* res = has_residual ? reinterpret_cast<const float*>(16) : nullptr;
+    const int rc = conv_forward_impl(nullptr, nullptr, split_weights != 0, nullptr, res, nullptr, B, H, W, Cin, Cout, kh, kw, stride,
+                                     pad, flags, nullptr, &bytes);
+    return rc ? (long long)rc : (long long)bytes;
+}
+int mdb_set_workspace(void* buf, unsigned long long bytes) {
+    DeviceState& d = g_dev[current_device()];
+    d.ws = static_cast<float*>(buf);
+    d.ws_bytes = buf ? (size_t)bytes : 0;
+    return 0;
+}
+int mdb_conv2d_dgrad_f32(const float* dy, const float* w_packed, const float* residual, const float* relu_mask,
+                         float* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
+                         int flags, void* stream) {
+    return conv_dgrad_impl(dy, w_packed, false, residual, relu_mask, dx, B, H, W, Cin, Cout, kh, kw, stride, pad, flags, stream);
+}
+int mdb_conv2d_dgrad_bf16x3(const float* dy, const void* w_split_t, const float* residual, const float* relu_mask,
+                            float* dx, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad,
+                            int flags, void* stream) {
+    return conv_dgrad_impl(dy, w_split_t, true, residual, relu_mask, dx, B, H, W, Cin, Cout, kh, kw, stride, pad, flags, stream);
 }
 
 // dw_packed[tap][Cout][Cin] (+)= rowscale[co] * sum_{b,oy,ox} dy[b,oy,ox,co] * x[b, oy*s+ky-pad, ox*s+kx-pad, ci]
@@ -890,7 +1136,7 @@ int mdb_conv2d_wgrad_bias_f32(const float* dy, const float* x, const float* rows
     }
     const int taps = kh * kw;
     static const bool tmem_a = getenv("MDB_NO_TMEM_A") == nullptr;
-    const bool fused_db = db && g_precision == 1 && tmem_a;
+    const bool fused_db = db && g_precision != 0 && tmem_a;
     if (!accumulate) {
         // db directly behind dw_packed (as monodetr_b200.tc allocates them): one memset node instead of two
         const bool adjacent = fused_db && db == dw_packed + (size_t)taps * Cout * Cin;
@@ -947,7 +1193,7 @@ int mdb_conv2d_wgrad_bias_f32(const float* dy, const float* x, const float* rows
         if (rc) return rc;
     }
     dim3 grid((Cin + bn - 1) / bn, (Cout + BM - 1) / BM, taps * splits);
-    rc = (g_precision == 1) ? (tmem_a ? launch_tc<128, 4, 1, true, true, true>(ma, mb, p, grid, stream)
+    rc = (g_precision != 0) ? (tmem_a ? launch_tc<128, 4, 1, true, true, true>(ma, mb, p, grid, stream)
                                       : launch_tc<128, 3, 1, true, true>(ma, mb, p, grid, stream))
          : (bn == 256)      ? launch_tc<256, 4, 1, true, false>(ma, mb, p, grid, stream)
                             : launch_tc<128, 5, 1, true, false>(ma, mb, p, grid, stream);

@@ -90,6 +90,78 @@ __global__ void unpack_wgrad_multi_kernel(const __grid_constant__ MultiTable tb)
     }
 }
 
+
+// ---- bf16x3 operand packing -----------------------------------------------------------------------------------------
+// Weights of the tensor-core GEMMs, split ONCE per step into error-compensated bf16 pairs and laid out the way the
+// kernels' B operand wants them (conv_gemm.cu, BF variant): for every (tap, row n, 32-wide k-block) one 128-byte row
+// [hi(k0..k31) | lo(k0..k31)], hi = bf16_rn(v), lo = bf16_rn(v - hi), v = w * (scale ? scale[o] : 1).
+//   wf[tap][o][ceil(I/32)][64]   rows = output channels, k = input channels   (fprop)
+//   wd[tap][i][ceil(O/32)][64]   rows = input channels,  k = output channels  (dgrad: the transposed weight, K-major)
+// Padding k positions (beyond I resp. O) are written as zeros.  One block = one 32(o) x 32(i) tile over all taps, staged in
+// shared memory so that reads of the source and writes of both layouts are coalesced.
+constexpr int kSplitMaxTaps = 9;
+struct SplitTable {
+    const float* src[kMaxMulti];
+    const float* scale[kMaxMulti];
+    uint32_t* wf[kMaxMulti];
+    uint32_t* wd[kMaxMulti];
+    int O[kMaxMulti], I[kMaxMulti], taps[kMaxMulti], tile_begin[kMaxMulti + 1];
+    int n, packed_src;
+};
+
+__device__ __forceinline__ uint32_t bf16x2_rn(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+__global__ void __launch_bounds__(256) pack_split_bf16_kernel(const __grid_constant__ SplitTable tb) {
+    __shared__ float tile[kSplitMaxTaps][32][33];
+    int k = 0;
+    while (k + 1 < tb.n && (int)blockIdx.x >= tb.tile_begin[k + 1]) ++k;
+    const int O = tb.O[k], I = tb.I[k], taps = tb.taps[k];
+    const int tiles_i = (I + 31) / 32;
+    const int lt = blockIdx.x - tb.tile_begin[k];
+    const int o0 = (lt / tiles_i) * 32, i0 = (lt % tiles_i) * 32;
+    const float* __restrict__ w = tb.src[k];
+    const float* __restrict__ scale = tb.scale[k];
+    // element (o, i, t): OIHW source = w[(o*I + i)*taps + t]; packed source = w[(t*O + o)*I + i]
+    for (int idx = threadIdx.x; idx < 32 * 32 * taps; idx += 256) {
+        int o, i, t;
+        if (tb.packed_src) { i = idx & 31; o = (idx >> 5) & 31; t = idx >> 10; }
+        else { t = idx % taps; const int r = idx / taps; i = r & 31; o = r >> 5; }
+        float v = 0.f;
+        if (o0 + o < O && i0 + i < I) {
+            v = tb.packed_src ? w[((size_t)t * O + o0 + o) * I + i0 + i] : w[((size_t)(o0 + o) * I + i0 + i) * taps + t];
+            if (scale) v *= scale[o0 + o];
+        }
+        tile[t][o][i] = v;
+    }
+    __syncthreads();
+    const int kbf = (I + 31) / 32, kbd = (O + 31) / 32;
+    uint32_t* __restrict__ wf = tb.wf[k];
+    uint32_t* __restrict__ wd = tb.wd[k];
+    for (int idx = threadIdx.x; idx < taps * 32 * 16; idx += 256) {
+        const int wq = idx & 15, r = (idx >> 4) & 31, t = idx >> 9;
+        if (o0 + r < O) {      // wf row (t, o0 + r), k-block i0 / 32: 32-bit words, 16 hi then 16 lo
+            const float a = tile[t][r][2 * wq], b = tile[t][r][2 * wq + 1];
+            const uint32_t h = bf16x2_rn(a, b);
+            const uint32_t l = bf16x2_rn(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xFFFF0000u));
+            uint32_t* row = wf + (((size_t)t * O + o0 + r) * kbf + (i0 >> 5)) * 32;
+            row[wq] = h;
+            row[16 + wq] = l;
+        }
+        if (wd && i0 + r < I) {   // wd row (t, i0 + r), k-block o0 / 32
+            const float a = tile[t][2 * wq][r], b = tile[t][2 * wq + 1][r];
+            const uint32_t h = bf16x2_rn(a, b);
+            const uint32_t l = bf16x2_rn(a - __uint_as_float(h << 16), b - __uint_as_float(h & 0xFFFF0000u));
+            uint32_t* row = wd + (((size_t)t * I + i0 + r) * kbd + (o0 >> 5)) * 32;
+            row[wq] = h;
+            row[16 + wq] = l;
+        }
+    }
+}
+
 // out[n] += sum_m x[m][n]; grid.x covers column groups of 32, grid.y row slabs.
 __global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long M, int N, int rows_per_block) {
     __shared__ float part[8][33];
@@ -149,6 +221,34 @@ int mdb_pack_conv_weights_multi_f32(int n, const float* const* w_oihw, const flo
             tb.O[k] = O[j]; tb.I[k] = I[j]; tb.taps[k] = taps[j];
         }
         pack_weight_multi_kernel<<<dim3(64, m), 256, 0, static_cast<cudaStream_t>(stream)>>>(tb, mdb_get_precision() == 0);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}
+
+
+// Multi-tensor split-pack for precision mode 2 (see pack_split_bf16_kernel); array arguments are HOST arrays.  wd may be NULL
+// (or hold NULL entries) when no data gradient will be taken.  src_packed: 0 = OIHW sources, 1 = [tap][O][I] sources.
+int mdb_pack_gemm_weights_bf16x3(int n, const float* const* w, const float* const* scale, void* const* wf, void* const* wd,
+                                 const int* O, const int* I, const int* taps, int src_packed, void* stream) {
+    if (n < 0 || (n > 0 && (!w || !wf || !O || !I || !taps))) return MDB_EINVAL;
+    for (int base = 0; base < n; base += kMaxMulti) {
+        SplitTable tb;
+        const int m = n - base < kMaxMulti ? n - base : kMaxMulti;
+        int tiles = 0;
+        for (int k = 0; k < m; ++k) {
+            const int j = base + k;
+            if (!w[j] || !wf[j] || O[j] <= 0 || I[j] <= 0 || taps[j] <= 0 || taps[j] > kSplitMaxTaps) return MDB_EINVAL;
+            tb.src[k] = w[j]; tb.scale[k] = scale ? scale[j] : nullptr;
+            tb.wf[k] = static_cast<uint32_t*>(wf[j]); tb.wd[k] = wd ? static_cast<uint32_t*>(wd[j]) : nullptr;
+            tb.O[k] = O[j]; tb.I[k] = I[j]; tb.taps[k] = taps[j];
+            tb.tile_begin[k] = tiles;
+            tiles += ((O[j] + 31) / 32) * ((I[j] + 31) / 32);
+        }
+        tb.tile_begin[m] = tiles;
+        tb.n = m; tb.packed_src = src_packed ? 1 : 0;
+        pack_split_bf16_kernel<<<tiles, 256, 0, static_cast<cudaStream_t>(stream)>>>(tb);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
     }
@@ -382,11 +482,13 @@ int mdb_stem_conv7x7_bn_relu_f32(const float* x, const float* w, const float* sc
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
     const int smem = (147 * ST_C + 3 * ST_IH * ST_IW) * (int)sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};               // per (function, device)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured[dev] = true;
     }
     dim3 grid((Wo + ST_TW - 1) / ST_TW, (Ho + ST_TH - 1) / ST_TH, B);
     // single-pass TF32 mode: the consumer is a tensor-core operand that expects round-to-nearest TF32 values

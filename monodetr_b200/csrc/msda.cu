@@ -486,13 +486,11 @@ msda_bwd_generic_kernel(const T* __restrict__ value, const int64_t* __restrict__
 }
 
 int num_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-    }
-    return sms;
+    static int sms[64] = {};                       // per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (sms[dev] == 0 && cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms[dev] = 148;
+    return sms[dev];
 }
 
 int grid_for(long long n_warps_needed, int blocks_per_sm) {

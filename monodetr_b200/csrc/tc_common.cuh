@@ -99,6 +99,21 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
         : "memory");
 }
 
+// TMA store (shared -> global, bulk async-group completion): the smem box must already be visible to the async proxy
+// (fence_proxy_async_smem after the generic-proxy writes).  Out-of-bounds parts of the box are clipped.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {   // at most N bulk groups of this thread still READING shared memory
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- tcgen05 ----------------------------------------------------------------------------------
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_in_smem) {   // one full warp
@@ -160,6 +175,31 @@ __device__ __forceinline__ void umma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, u
         : "memory");
 }
 
+// D[tmem] (+)= A[tmem: 128 lanes x 8 columns per k-step = 16 packed bf16, K-major] * B[smem desc, bf16], fp32 accumulate.
+__device__ __forceinline__ void umma_bf16_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// D[tmem] (+)= A[smem desc, bf16] * B[smem desc, bf16], fp32 accumulate.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// two fp32 -> one packed bf16x2 word, round-to-nearest-even; `lo` lands in bits [0,16), `hi` in bits [16,32)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 // ---- descriptors ------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (64 bit): [0,14) start>>4, [16,30) LBO>>4, [32,46) SBO>>4,
 // [46,48) version=1 (Blackwell), [61,64) layout (2 = SWIZZLE_128B).
@@ -179,6 +219,12 @@ __host__ __device__ constexpr uint64_t make_smem_desc_sw128(uint32_t smem_addr, 
 // [17,23) N>>3, [24,29) M>>4.
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_major, bool b_mn_major) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Instruction descriptor for kind::f16 with BF16 operands (a_format = b_format = 1), fp32 accumulate, both K-major.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_major = false, bool b_mn_major = false) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 

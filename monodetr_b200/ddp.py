@@ -15,7 +15,12 @@ class FlatGradBucket:
     """Two modes.  `views=True`: every .grad IS a view of the flat buffer (backward accumulates in place; one
     `zero()` per step; costs one small add kernel per parameter in AccumulateGrad).  `views=False` (default): backward
     produces ordinary gradients and `all_reduce()` first packs them with ONE multi-tensor copy, reduces the flat buffer
-    and leaves `.grad` pointing at the reduced views -- ~4 launches instead of 313."""
+    and leaves `.grad` pointing at the reduced views -- ~4 launches instead of 313.
+
+    CUDA-graph mode (`freeze_sources()` right after capturing fwd+bwd, views=False): every replay rewrites the captured
+    gradient tensors (`static_grads`); `all_reduce()` packs from THOSE and, like the eager mode, leaves `.grad` pointing
+    at the reduced views, so an optimizer stepping on `p.grad` always sees the rank-mean gradients.  The captured
+    tensors are remembered separately, so re-pointing `.grad` never changes what the next replay's pack reads."""
 
     def __init__(self, model, views=False):
         self.params = [p for n, p in model.named_parameters() if p.requires_grad and not any(s in n for s in _NEVER_USED)]
@@ -43,6 +48,11 @@ class FlatGradBucket:
     def freeze_sources(self):
         """Call once right after capturing fwd+bwd in a CUDA graph: replays rewrite these very tensors."""
         if not self.use_views:
+            flat_lo, flat_hi = self.flat.data_ptr(), self.flat.data_ptr() + self.flat.numel() * 4
+            for p in self.params:
+                if p.grad is not None and flat_lo <= p.grad.data_ptr() < flat_hi:
+                    raise RuntimeError("freeze_sources(): .grad already aliases the flat bucket (an eager all_reduce ran "
+                                       "before the capture); call bucket.zero() and capture again")
             self.static_grads = [p.grad if p.grad is not None else torch.zeros_like(v) for p, v in zip(self.params, self.views)]
 
     def _distributed(self):
@@ -56,9 +66,10 @@ class FlatGradBucket:
             torch._foreach_copy_(self.views, grads)
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
         self.flat.div_(dist.get_world_size())
-        if not self.use_views and self.static_grads is None:
+        if not self.use_views:
             for p, v in zip(self.params, self.views):
-                p.grad = v                                   # the optimizer sees the reduced gradients
+                if p.grad is not v:
+                    p.grad = v                               # the optimizer sees the reduced gradients (graph mode too)
 
 
 def broadcast_parameters(model, src=0):

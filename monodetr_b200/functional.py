@@ -61,10 +61,11 @@ def relu_backward(dy, y, scale=1.0):
     return out
 
 
-def dropout_raw(x, p, site):
+def dropout_raw(x, p, site, seed=None):
     x = x.contiguous()
     out = torch.empty_like(x)
-    _lib.check(_lib.lib().mdb_dropout_f32(_p(x), _p(out), x.numel(), float(p), _p(K.seed_tensor(x.device)), site, _s()), "dropout")
+    seed = seed if seed is not None else K.seed_tensor(x.device)
+    _lib.check(_lib.lib().mdb_dropout_f32(_p(x), _p(out), x.numel(), float(p), _p(seed), site, _s()), "dropout")
     _lib.count(1)
     return out
 
@@ -73,12 +74,13 @@ class _Dropout(Function):
     @staticmethod
     def forward(ctx, x, p, site):
         ctx.p, ctx.site = p, site
-        return dropout_raw(x, p, site)
+        ctx.seed = K.seed_tensor(x.device)          # this forward's snapshot: backward regenerates the SAME mask
+        return dropout_raw(x, p, site, ctx.seed)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        return dropout_raw(dy, ctx.p, ctx.site), None, None
+        return dropout_raw(dy, ctx.p, ctx.site, ctx.seed), None, None
 
 
 def dropout(x, p, training, site):
@@ -99,14 +101,17 @@ class _Linear(Function):
         x2 = x.reshape(-1, K_)
         if not x2.is_contiguous():
             x2 = x2.contiguous()
-        wr = tc.round_tf32(w.contiguous())
+        split = tc.get_precision() == "bf16x3"
+        # bf16x3: the weight as (hi, lo) bf16 pairs in both operand layouts, split once per model forward (tc.prepacked)
+        wr = tc.lookup_split(w) if split else tc.round_tf32(w.contiguous())
         r2 = None
         if residual is not None:
             r2 = residual.reshape(-1, N).contiguous()
         # the forward kernel takes any N (ragged right edge handled in its epilogue); only the backward operands need
         # 16-byte row pitches, so padding to a multiple of 4 happens there
         y = tc.linear_forward(x2, wr, None if b is None else b.contiguous(), r2, relu=relu)
-        ctx.save_for_backward(x2, wr, y if relu else None)
+        ctx.save_for_backward(x2, None if split else wr, y if relu else None)
+        ctx.split_w = wr if split else None
         ctx.meta = (x.shape, N, Np, b is not None, residual is not None, relu)
         return y.view(*x.shape[:-1], N)
 
@@ -114,6 +119,8 @@ class _Linear(Function):
     @once_differentiable
     def backward(ctx, dy):
         x2, wr, y = ctx.saved_tensors
+        if ctx.split_w is not None:
+            wr = ctx.split_w
         xshape, N, Np, has_b, has_res, relu = ctx.meta
         dy2 = dy.reshape(-1, N).contiguous()
         if relu:
@@ -121,7 +128,8 @@ class _Linear(Function):
         dres_src = dy2
         if Np != N:
             dy2 = F.pad(dy2, (0, Np - N))
-            wr = F.pad(wr, (0, 0, 0, Np - N))
+            if ctx.split_w is None:                 # (a SplitW's k-blocks are zero-padded to 32 already)
+                wr = F.pad(wr, (0, 0, 0, Np - N))
         dx = dw = db = dres = None
         want_db = has_b and ctx.needs_input_grad[2]
         fork = None
@@ -158,6 +166,14 @@ class _Conv2d(Function):
     def forward(ctx, x, w, b, stride, pad):
         O, I, kh, kw = w.shape
         Op = _pad4(O)
+        if tc.get_precision() == "bf16x3":
+            # split (hi, lo) bf16 operands straight from the OIHW parameter; the forward writes a ragged Cout itself
+            sw = tc.lookup_split(w)
+            y = tc.conv2d_forward(x, sw, None if b is None else b.contiguous(), None, kh, kw, stride, pad)
+            ctx.save_for_backward(x)
+            ctx.split_w = sw
+            ctx.meta = (O, Op, kh, kw, stride, pad, b is not None)
+            return y
         wp = tc.pack_weight(w.contiguous())                      # (taps, O, I), rounded to TF32
         bp = b
         if Op != O:
@@ -165,13 +181,17 @@ class _Conv2d(Function):
             bp = None if b is None else F.pad(b, (0, Op - O))
         y = tc.conv2d_forward(x, wp, None if bp is None else bp.contiguous(), None, kh, kw, stride, pad)
         ctx.save_for_backward(x, wp)
+        ctx.split_w = None
         ctx.meta = (O, Op, kh, kw, stride, pad, b is not None)
         return y if Op == O else y[..., :O].contiguous()
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x, wp = ctx.saved_tensors
+        if ctx.split_w is not None:
+            (x,), wp = ctx.saved_tensors, ctx.split_w
+        else:
+            x, wp = ctx.saved_tensors
         O, Op, kh, kw, stride, pad, has_b = ctx.meta
         if Op != O:
             dy = F.pad(dy, (0, Op - O))
@@ -205,7 +225,8 @@ class _AddLayerNorm(Function):
     def forward(ctx, x, res, gamma, beta, eps, drop_p, site):
         x = x.contiguous()
         res = None if res is None else res.contiguous()
-        y, mean, rstd = K.add_layernorm_forward(x, res, gamma, beta, eps, drop_p, site)
+        ctx.seed = K.seed_tensor(x.device) if drop_p > 0 else None
+        y, mean, rstd = K.add_layernorm_forward(x, res, gamma, beta, eps, drop_p, site, ctx.seed)
         ctx.save_for_backward(x, res, gamma, mean, rstd)
         ctx.meta = (drop_p, site)
         return y
@@ -215,7 +236,7 @@ class _AddLayerNorm(Function):
     def backward(ctx, dy):
         x, res, gamma, mean, rstd = ctx.saved_tensors
         drop_p, site = ctx.meta
-        dx, dres, dg, db = K.add_layernorm_backward(dy, x, res, gamma, mean, rstd, drop_p, site)
+        dx, dres, dg, db = K.add_layernorm_backward(dy, x, res, gamma, mean, rstd, drop_p, site, ctx.seed)
         return dx, (dres if res is not None else None), dg, db, None, None, None
 
 
@@ -250,7 +271,8 @@ def groupnorm_nhwc(x, gamma, beta, G=32, eps=1e-5, relu=False):
 class _Attention(Function):
     @staticmethod
     def forward(ctx, q, k, v, kpm, drop_p, site):
-        out, lse, kp = K.attention_forward(q, k, v, kpm, drop_p, site)
+        ctx.seed = K.seed_tensor(q.device) if drop_p > 0 else None
+        out, lse, kp = K.attention_forward(q, k, v, kpm, drop_p, site, ctx.seed)
         ctx.save_for_backward(q, k, v, kp, out, lse)
         ctx.meta = (drop_p, site)
         return out
@@ -260,7 +282,7 @@ class _Attention(Function):
     def backward(ctx, dout):
         q, k, v, kp, out, lse = ctx.saved_tensors
         drop_p, site = ctx.meta
-        dq, dk, dv = K.attention_backward(q, k, v, kp, out, lse, dout, drop_p, site)
+        dq, dk, dv = K.attention_backward(q, k, v, kp, out, lse, dout, drop_p, site, ctx.seed)
         return dq, dk, dv, None, None, None
 
 
@@ -288,14 +310,17 @@ class _MsdaPrep(Function):
         _lib.check(_lib.lib().mdb_msda_prep_forward_f32(_p(off), _p(logits), _p(refc), _p(shapes), B, Lq, M, L, P, rd, _p(loc),
                                                         _p(attn), _s()), "msda_prep_forward")
         _lib.count(1)
-        ctx.save_for_backward(attn, refc, shapes)
+        # 6-d reference boxes that require grad (not on the model path, where they are detached -- depthaware_transformer.py
+        # :613 -- but a custom decoder may pass them): keep the offsets for the box gradient
+        keep_off = rd == 6 and ref.requires_grad
+        ctx.save_for_backward(attn, refc, shapes, off if keep_off else None)
         ctx.meta = (B, Lq, M, L, P, rd, off.shape, logits.shape)
         return loc, attn
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dloc, dattn):
-        attn, refc, shapes = ctx.saved_tensors
+        attn, refc, shapes, off = ctx.saved_tensors
         B, Lq, M, L, P, rd, oshape, lshape = ctx.meta
         dloc = dloc.contiguous()
         dattn = dattn.contiguous()
@@ -306,9 +331,15 @@ class _MsdaPrep(Function):
         _lib.count(1)
         dref = None
         if ctx.needs_input_grad[2]:
-            if rd != 2:
-                raise RuntimeError("gradient wrt 6-d reference boxes is not needed on this path (they are detached)")
-            dref = dloc.sum(dim=(2, 4))                                   # (B, Lq, L, 2)
+            if rd == 2:
+                dref = dloc.sum(dim=(2, 4))                               # (B, Lq, L, 2)
+            else:
+                # loc = ref_xy + off / P * (l + r, t + b) / 2 (ms_deform_attn.py:154-155; 2::2 -> (l, t), 3::2 -> (r, b)):
+                # d/d(cx, cy) = sum dloc ; d/dl = d/dr = sum dloc_x off_x / (2P) ; d/dt = d/db = sum dloc_y off_y / (2P).
+                # Small reductions in plain torch: this branch is never taken by the model (boxes are detached there).
+                dxy = dloc.sum(dim=(2, 4))
+                dwh = (dloc * off.view(B, Lq, M, L, P, 2)).sum(dim=(2, 4)) * (0.5 / P)   # (B, Lq, L, 2) = (d(l+r), d(t+b))
+                dref = torch.stack((dxy[..., 0], dxy[..., 1], dwh[..., 0], dwh[..., 0], dwh[..., 1], dwh[..., 1]), -1)
         return doff, dlogits, dref, None, None, None, None
 
 

@@ -12,7 +12,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import functional as Fn
+from . import functional as Fn, kernels as K, tc
 from .backbone import build_backbone
 from .depth_predictor import DepthPredictor
 from .depthaware_transformer import MLP, build_depthaware_transformer, inverse_sigmoid
@@ -107,8 +107,32 @@ class MonoDETR(nn.Module):
         self.angle_embed = _get_clones(self.angle_embed, num_pred)
         self.depth_embed = _get_clones(self.depth_embed, num_pred)
 
+    _NO_PREPACK = ("backbone", "sa_v_proj", "query_scale", "ref_point_head", "sa_qcontent_proj", "sa_qpos_proj",
+                   "sa_kcontent_proj", "sa_kpos_proj")
+
+    def _gemm_weights(self):
+        """Every nn.Linear / nn.Conv2d / in_proj slice the forward feeds to the tensor-core GEMMs as-is (the ResNet body
+        splits its own BN-folded weights; summed decoder projections are split where they are formed)."""
+        out = []
+        with torch.no_grad():
+            for name, m in self.named_modules():
+                if any(k in name for k in self._NO_PREPACK):
+                    continue
+                if isinstance(m, nn.MultiheadAttention):
+                    w, c = m.in_proj_weight, m.embed_dim
+                    out += [w[:c], w[c:], w[c:2 * c], w[2 * c:], w[:2 * c]]
+                elif isinstance(m, (nn.Linear, nn.Conv2d)):
+                    out.append(m.weight)
+        return out
+
     def forward(self, images, calibs, targets, img_sizes, dn_args=None):
         """images (B, 3, H, W) fp32 NCHW; calibs (B, 3, 4); targets / dn_args ignored; img_sizes (B, 2) [W, H]."""
+        if self.training and images.is_cuda:
+            K.begin_forward(images.device)          # new dropout masks every training forward (device-side, graph-safe)
+        with tc.prepacked(self._gemm_weights() if images.is_cuda else []):
+            return self._forward(images, calibs, targets, img_sizes, dn_args)
+
+    def _forward(self, images, calibs, targets, img_sizes, dn_args=None):
         features, pos = self.backbone(images)                                      # NHWC maps, (HW, C) tables
         srcs = [self.input_proj[l](feat) for l, feat in enumerate(features)]
         for l in range(len(srcs), self.num_feature_levels):
@@ -152,10 +176,40 @@ class MonoDETR(nn.Module):
         return out
 
 
+def _reference_criterion(cfg):
+    """SetCriterion + HungarianMatcher exactly as the reference's build() assembles them (monodetr.py:578-612), taken from
+    the reference package when it is importable (`lib.models.monodetr` on PYTHONPATH, as under tools/train_val.py).  The
+    criterion sits AFTER the hot path and is used unchanged; returns None when the package is absent."""
+    try:
+        from lib.models.monodetr.matcher import build_matcher
+        from lib.models.monodetr.monodetr import SetCriterion
+    except Exception:          # not installed / not importable on this torch: the caller gets (model, None)
+        return None
+    matcher = build_matcher(cfg)
+    weight_dict = {"loss_ce": cfg["cls_loss_coef"], "loss_bbox": cfg["bbox_loss_coef"], "loss_giou": cfg["giou_loss_coef"],
+                   "loss_dim": cfg["dim_loss_coef"], "loss_angle": cfg["angle_loss_coef"], "loss_depth": cfg["depth_loss_coef"],
+                   "loss_center": cfg["3dcenter_loss_coef"], "loss_depth_map": cfg["depth_map_loss_coef"]}
+    if cfg.get("use_dn"):
+        weight_dict.update({"tgt_loss_ce": cfg["cls_loss_coef"], "tgt_loss_bbox": cfg["bbox_loss_coef"],
+                            "tgt_loss_giou": cfg["giou_loss_coef"], "tgt_loss_angle": cfg["angle_loss_coef"],
+                            "tgt_loss_center": cfg["3dcenter_loss_coef"]})
+    if cfg["aux_loss"]:
+        aux = {}
+        for i in range(cfg["dec_layers"] - 1):
+            aux.update({k + f"_{i}": v for k, v in weight_dict.items()})
+        aux.update({k + "_enc": v for k, v in weight_dict.items()})
+        weight_dict.update(aux)
+    losses = ["labels", "boxes", "cardinality", "depths", "dims", "angles", "center", "depth_map"]
+    criterion = SetCriterion(cfg["num_classes"], matcher=matcher, weight_dict=weight_dict, focal_alpha=cfg["focal_alpha"],
+                             losses=losses)
+    return criterion.to(torch.device(cfg["device"]))
+
+
 def build(cfg, criterion_builder=None):
-    """Same contract as the reference's build(cfg) (:550-614): returns (model, criterion).  The criterion
-    (SetCriterion + HungarianMatcher) is outside the hot path: pass `criterion_builder(cfg)` -- e.g. the
-    reference's own -- or get None."""
+    """Same contract as the reference's build(cfg) (:550-614): returns (model, criterion).  The criterion (SetCriterion +
+    HungarianMatcher) is outside the hot path: `criterion_builder(cfg)` if given, else the reference's own
+    classes assembled as the reference does when `lib.models.monodetr` is importable (the situation inside
+    tools/train_val.py), else None (stand-alone use of the model, e.g. bench.py)."""
     backbone = build_backbone(cfg)
     depthaware_transformer = build_depthaware_transformer(cfg)
     depth_predictor = DepthPredictor(cfg)
@@ -163,7 +217,12 @@ def build(cfg, criterion_builder=None):
                      num_queries=cfg["num_queries"], aux_loss=cfg["aux_loss"], num_feature_levels=cfg["num_feature_levels"],
                      with_box_refine=cfg["with_box_refine"], two_stage=cfg["two_stage"], init_box=cfg["init_box"],
                      use_dab=cfg["use_dab"], two_stage_dino=cfg["two_stage_dino"])
-    criterion = criterion_builder(cfg) if criterion_builder is not None else None
+    if criterion_builder is not None:
+        criterion = criterion_builder(cfg)
+    elif "cls_loss_coef" in cfg:                   # a full configs/monodetr.yaml model section (loss weights present)
+        criterion = _reference_criterion(cfg)
+    else:
+        criterion = None
     return model, criterion
 
 

@@ -10,16 +10,22 @@ pytestmark = pytest.mark.gpu
 TOL = 2e-3      # rebound per precision mode by the fixture below
 
 
-@pytest.fixture(autouse=True, params=["tf32x3", "tf32"])
+DEFAULT_PRECISION = None
+
+
+@pytest.fixture(autouse=True, params=["bf16x3", "tf32x3", "tf32"])
 def precision(request):
-    """tf32x3 (default, error-compensated): fp32-class accuracy (measured 1.7e-5 at K=2304 and 1.1e-4 at K=18432: the tensor core's
-    internal accumulation truncates), tolerance 3e-4; tf32 (single pass): 2e-3."""
+    """tf32x3 (error-compensated TF32): fp32-class accuracy (measured 1.7e-5 at K=2304 and 1.1e-4 at K=18432: the tensor core's
+    internal accumulation truncates); bf16x3 (error-compensated BF16 for fprop / dgrad with pre-split weights, dropped terms
+    ~2^-17 per product; wgrad is 3xTF32): both held to 3e-4.  tf32 (single pass): 2e-3."""
     from monodetr_b200 import tc
-    global TOL
+    global TOL, DEFAULT_PRECISION
+    if DEFAULT_PRECISION is None:
+        DEFAULT_PRECISION = tc.get_precision()
     tc.set_precision(request.param)
-    TOL = 3e-4 if request.param == "tf32x3" else 2e-3
+    TOL = 2e-3 if request.param == "tf32" else 3e-4
     yield request.param
-    tc.set_precision("tf32x3")
+    tc.set_precision(DEFAULT_PRECISION)
 
 
 def _ref_setup():
@@ -107,6 +113,14 @@ def test_conv_forward_backward(cfg):
     wp = tc.pack_weight(w, scale)
     ref_wp = (w * scale.view(-1, 1, 1, 1)).permute(2, 3, 0, 1).reshape(k * k, Cout, Cin)
     assert _relerr(wp, ref_wp.contiguous()) < 6e-4          # (rounded to nearest TF32 in 'tf32' mode)
+    if tc.get_precision() == "bf16x3":
+        # model path: operands split straight from the OIHW parameter with the BN scale folded in (the fp32 `wp` passed
+        # further down is split on the fly from the packed layout: both source layouts must give the same bits)
+        sw = tc.split_weights([w], [scale])[0]
+        sw2 = tc.split_weights([wp], packed_src=True)[0]
+        assert torch.equal(sw.wf, sw2.wf) and torch.equal(sw.wd, sw2.wd)
+        y = tc.conv2d_forward(x_nhwc, sw, bias, None, k, k, s, pad, relu=False)
+        assert _report("fwd (SplitW)", y.permute(0, 3, 1, 2), F.conv2d(x, w * scale.view(-1, 1, 1, 1), bias, stride=s, padding=pad)) < TOL
     ws = w * scale.view(-1, 1, 1, 1)
     ref = F.conv2d(x, ws, bias, stride=s, padding=pad)
     res = torch.randn_like(ref)
@@ -161,6 +175,52 @@ def test_functional_linear_autograd_ragged_n(M, N, K, relu):
     assert _report("dx", gx, rx) < TOL
     assert _report("dw", gw, rw) < TOL
     assert _report("db", gb, rb) < TOL
+
+
+@pytest.mark.parametrize("O,I,taps", [(256, 256, 1), (81, 256, 1), (3, 256, 1), (64, 64, 9), (36, 32, 9), (130, 70, 1)])
+def test_split_weights_layout_and_reconstruction(O, I, taps):
+    """mdb_pack_gemm_weights_bf16x3: both operand layouts, hi = bf16_rn(v), lo = bf16_rn(v - hi), zero padding; hi + lo
+    reproduces the fp32 weight to 2^-16 relative."""
+    from monodetr_b200 import tc
+    g = torch.Generator(device="cuda").manual_seed(O * 31 + I + taps)
+    kk = int(taps ** 0.5)
+    w = torch.randn(O, I, kk, kk, device="cuda", generator=g)
+    sc = torch.rand(O, device="cuda", generator=g) + 0.5
+    sw = tc.split_weights([w], [sc])[0]
+    v = (w * sc.view(-1, 1, 1, 1)).reshape(O, I, taps).permute(2, 0, 1)                     # (taps, O, I)
+    hi = v.to(torch.bfloat16)
+    lo = (v - hi.float()).to(torch.bfloat16)
+    kbf, kbd = (I + 31) // 32, (O + 31) // 32
+    pad_i = kbf * 32 - I
+    ref_f = torch.stack((torch.nn.functional.pad(hi, (0, pad_i)).view(taps, O, kbf, 32),
+                         torch.nn.functional.pad(lo, (0, pad_i)).view(taps, O, kbf, 32)), 3).reshape(taps, O, kbf, 64)
+    assert torch.equal(sw.wf, ref_f)
+    pad_o = kbd * 32 - O
+    hit, lot = hi.transpose(1, 2), lo.transpose(1, 2)                                          # (taps, I, O)
+    ref_d = torch.stack((torch.nn.functional.pad(hit, (0, pad_o)).reshape(taps, I, kbd, 32),
+                         torch.nn.functional.pad(lot, (0, pad_o)).reshape(taps, I, kbd, 32)), 3).reshape(taps, I, kbd, 64)
+    assert torch.equal(sw.wd, ref_d)
+    rec = sw.wf.view(taps, O, kbf, 2, 32).float().sum(3).reshape(taps, O, kbf * 32)[..., :I]
+    assert float((rec - v).abs().max() / v.abs().max()) < 2 ** -16
+
+
+def test_prepacked_context_lookup():
+    """tc.prepacked: one multi-tensor split, lookups hit inside the context only."""
+    from monodetr_b200 import tc
+    prev = tc.get_precision()
+    tc.set_precision("bf16x3")
+    try:
+        w = torch.randn(768, 256, device="cuda")
+        lin = torch.randn(24, 256, device="cuda")
+        with tc.prepacked([w[:256], w[256:], lin]):
+            a = tc.lookup_split(w[:256])
+            assert a is tc.lookup_split(w[:256]) and a.shape == (1, 256, 256)
+            assert tc.lookup_split(w[256:]).shape == (1, 512, 256)
+            assert tc.lookup_split(lin).shape == (1, 24, 256)
+            assert torch.equal(a.wf, tc.split_weights([w[:256]])[0].wf)
+        assert tc.lookup_split(w[:256]) is not a                      # outside: split on the fly
+    finally:
+        tc.set_precision(prev)
 
 
 def test_multi_tensor_pack_unpack():

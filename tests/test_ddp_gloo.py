@@ -33,6 +33,26 @@ def _worker(rank, world, store_path, q, views):
     dist.all_gather(gathered, local)
     expect = sum(gathered) / world
     ok = torch.allclose(bucket.flat, expect, atol=1e-6) and model["a"].weight.grad.data_ptr() == bucket.flat.data_ptr()
+    if not views:
+        # CUDA-graph mode: a "replay" rewrites the captured gradient tensors in place; after all_reduce() an optimizer
+        # reading p.grad must see the rank mean, and the captured sources must stay what the next replay writes
+        bucket.zero()
+        model["b"](model["a"](x)).sum().backward()
+        bucket.freeze_sources()
+        srcs = [g for g in bucket.static_grads]
+        for step in range(2):
+            for g in srcs:                            # the replay: same tensors, new values
+                g.copy_(torch.full_like(g, float((rank + 1) * (step + 1))))
+            bucket.all_reduce()
+            want = (1 + 2) * (step + 1) / world
+            for p in bucket.params:
+                ok = ok and torch.allclose(p.grad, torch.full_like(p.grad, want))
+            ok = ok and all(a is b for a, b in zip(srcs, bucket.static_grads))
+        try:                                          # freezing sources that alias the bucket is refused, not silently wrong
+            bucket.freeze_sources()
+            ok = False
+        except RuntimeError:
+            pass
     q.put((rank, bool(ok), w0))
     dist.barrier()                                # nobody tears its sockets down while the peer is still communicating
     dist.destroy_process_group()

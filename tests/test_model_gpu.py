@@ -16,6 +16,16 @@ OUT_KEYS = ("pred_logits", "pred_boxes", "pred_3d_dim", "pred_depth", "pred_angl
 TOL = 1e-3
 
 
+@pytest.fixture(autouse=True, params=["bf16x3", "tf32x3"])
+def precision(request):
+    """Both error-compensated tensor-core modes must hold the north star's 1e-3 on the whole model."""
+    from monodetr_b200 import tc
+    prev = tc.get_precision()
+    tc.set_precision(request.param)
+    yield request.param
+    tc.set_precision(prev)
+
+
 def _model(dropout=0.0):
     from monodetr_b200 import build_monodetr
     from monodetr_b200.monodetr import DEFAULT_MODEL_CFG

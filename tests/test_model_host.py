@@ -78,3 +78,24 @@ def test_state_dict_matches_unmodified_reference(model):
     ref_train = {n for n, p in ref.named_parameters() if p.requires_grad}
     mine_train = {n for n, p in model.named_parameters() if p.requires_grad}
     assert ref_train == mine_train
+
+
+@pytest.mark.reference
+def test_build_returns_the_reference_criterion_when_importable():
+    """B2: build_monodetr(cfg) -> (model, criterion) like monodetr.py:550-614; with the reference package importable
+    (as inside tools/train_val.py) the criterion is the reference's SetCriterion with the reference's weight_dict."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import warnings
+    warnings.filterwarnings("ignore")
+    import ref_shims
+    pkg = ref_shims.install()
+    cfg = ref_shims.load_cfg()["model"]
+    _, ref_crit = pkg.build_monodetr(cfg)
+    from monodetr_b200 import build_monodetr
+    _, crit = build_monodetr(cfg)
+    assert type(crit) is type(ref_crit)
+    assert crit.weight_dict == ref_crit.weight_dict and crit.losses == ref_crit.losses
+    assert crit.focal_alpha == ref_crit.focal_alpha and crit.num_classes == ref_crit.num_classes
+    # without loss weights in the cfg (stand-alone model use) there is nothing to build a criterion from
+    from monodetr_b200.monodetr import DEFAULT_MODEL_CFG
+    assert build_monodetr(DEFAULT_MODEL_CFG)[1] is None

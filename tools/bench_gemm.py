@@ -37,13 +37,13 @@ def timeit(fn, n=10):
     return e0.elapsed_time(e1) / n * 1e3   # us
 
 
-for mode in (("tf32x3",) if os.environ.get("MDB_ONLY_X3") else ("tf32x3", "tf32")):
+for mode in tuple(os.environ["MDB_MODES"].split(",")) if os.environ.get("MDB_MODES") else (("tf32x3",) if os.environ.get("MDB_ONLY_X3") else ("bf16x3", "tf32x3", "tf32")):
     tc.set_precision(mode)
     print(f"== {mode}")
     for name, H, W, Cin, Cout, k, s in SHAPES:
         x = torch.randn(B, H, W, Cin, device="cuda")
         w = torch.randn(Cout, Cin, k, k, device="cuda") / (Cin * k * k) ** 0.5
-        wp = tc.pack_weight(w)
+        wp = tc.split_weights([w])[0] if mode == "bf16x3" else tc.pack_weight(w)
         pad = k // 2
         y = tc.conv2d_forward(x, wp, None, None, k, k, s, pad)
         dy = torch.randn_like(y)

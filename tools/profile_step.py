@@ -27,7 +27,6 @@ def step():
         return
     for p in model.parameters():
         p.grad = None
-    K.advance_seed(images.device)
     out = model(images, calibs, None, sizes)
     surrogate_loss(out).backward()
 
