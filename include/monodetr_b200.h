@@ -56,6 +56,12 @@ int mdb_msda_backward_f32(const float* value, const int64_t* spatial_shapes, con
                           const float* sampling_loc, const float* attn_weight, const float* grad_out,
                           int B, int S, int M, int D, int L, int Lq, int P,
                           float* grad_value, float* grad_loc, float* grad_attn, void* stream);
+/* Same, with a HOST copy of spatial_shapes (L x 2 int64; same values as the device tensor): lets the launcher size the
+ * shared-memory accumulators of the encoder-sized fast path (coarse levels privatised per CTA); NULL = mdb_msda_backward_f32. */
+int mdb_msda_backward_hs_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
+                             const int64_t* host_spatial_shapes, const float* sampling_loc, const float* attn_weight,
+                             const float* grad_out, int B, int S, int M, int D, int L, int Lq, int P,
+                             float* grad_value, float* grad_loc, float* grad_attn, void* stream);
 int mdb_msda_backward_f64(const double* value, const int64_t* spatial_shapes, const int64_t* level_start,
                           const double* sampling_loc, const double* attn_weight, const double* grad_out,
                           int B, int S, int M, int D, int L, int Lq, int P,

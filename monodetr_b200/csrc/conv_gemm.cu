@@ -89,11 +89,18 @@ struct TcParams {
 //                   patch read-back and the 8 predicated STG.128 per chunk of the register path -- which made every GEMM
 //                   with K <= 512 epilogue-bound (~1750 cycles per 32x32 chunk, gpurun r2 timelines) -- disappear; edge
 //                   clipping is done by the TMA unit.
+//                   TS == 2 adds the residual and / or ReLU-mask operands (ResNet conv3 + identity, every masked dgrad): their
+//                   32x32 boxes are TMA-LOADED into the warp's patches two chunks ahead (3 buffers, mbarrier per buffer), each
+//                   lane combines its row in place and the patch goes out through the same bulk store.
+//                   TS == 3: both operands (two patches per buffer).  TS kernels run EW = 8 epilogue warps (two per TMEM lane
+//                   quarter, alternating 32-column chunks): the per-chunk latencies (TMEM load, proxy fence, bulk-store issue,
+//                   operand loads in flight) are what bounds the epilogue, and they parallelise across warps.
 template <int BN, int STAGES, int MODE /*0 fprop/dgrad, 1 wgrad*/, bool B_MN, bool SPLIT, bool TA = false, bool BF = false,
-          bool TS = false>
-__global__ void __launch_bounds__(SPLIT ? 192 + 32 * kEpiWarps : 192)
+          int TS = 0, int EW = kEpiWarps>
+__global__ void __launch_bounds__(SPLIT ? 192 + 32 * EW : 192)
 tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                    const __grid_constant__ CUtensorMap mapO, const __grid_constant__ TcParams p) {
+                    const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapR,
+                    const __grid_constant__ CUtensorMap mapM, const __grid_constant__ TcParams p) {
     constexpr bool A_MN = (MODE == 1);
     constexpr int kTileBBytes = BN * 128;
     constexpr int kRawBytes = kTileABytes + kTileBBytes;          // what TMA delivers per stage
@@ -104,22 +111,27 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // 128 B/clk, profiles/r01_conv_gemm_timeline_k256.txt) -- and frees the smem for one more pipeline stage.
     // TMEM columns: [0, 2*BN) two accumulators, then per stage 32 columns raw A + 32 columns lo A.
     static_assert(!TA || SPLIT, "TMEM-resident A: 3xTF32 kernels only");
-    static_assert(!BF || (TA && MODE == 0 && !B_MN), "bf16x3: fprop / dgrad with K-major pre-split weights");
+    static_assert(!BF || (TA && B_MN == (MODE == 1)), "bf16x3: fprop / dgrad with K-major pre-split weights, or wgrad");
+    // bf16x3 wgrad: X arrives fp32 MN-major like dY; the splitter transposes it into a K-major [n][hi 32 | lo 32] bf16 tile
+    // (the layout the packed weights have in fprop) behind the raw tiles, so the MMA side is identical to fprop's.
+    constexpr bool B_DESC_MN = B_MN && !BF;
     constexpr int kAColsPerStage = BF ? 32 : 64;                  // TMEM columns of one stage's A operand (hi + lo)
     static_assert(!TA || 2 * BN + kAColsPerStage * STAGES <= 512, "TMEM budget");
-    constexpr int kStageBytes = BF ? kRawBytes : (TA ? kTileABytes + 2 * kTileBBytes : (SPLIT ? 2 * kRawBytes : kRawBytes));  // + the lo tiles
+    constexpr int kStageBytes = BF ? kRawBytes + (MODE == 1 ? kTileBBytes : 0) : (TA ? kTileABytes + 2 * kTileBBytes : (SPLIT ? 2 * kRawBytes : kRawBytes));  // + the lo tiles
     constexpr int kBLoOff = TA ? kTileBBytes : kRawBytes;          // B lo relative to B raw
     constexpr int kTmemCols = TA ? 512 : 2 * BN;
     constexpr int kEpiWarp0 = SPLIT ? 6 : 2;                        // first epilogue warp
-    constexpr int EPI = SPLIT ? kEpiWarps : 4;                      // epilogue warps
+    constexpr int EPI = SPLIT ? EW : 4;                             // epilogue warps
     static_assert(!(MODE == 1) || B_MN, "wgrad reads both operands MN-major");
 
     // NOTE: index the extern array directly.  Rounding the pointer up through uintptr_t made the compiler lose the
     // shared address space and emit GENERIC ld/st for every smem access of the splitter and the epilogue (measured:
     // ~2000 cycles per 32-column epilogue chunk).  The kernel has no static smem, so the dynamic window starts at the
     // CTA's (1024-byte aligned) shared base; the assumption is checked once below.
-    static_assert(!TS || MODE == 0, "TMA-store epilogue: fprop / dgrad");
-    constexpr int kTsPatchBytes = TS ? 2 * (SPLIT ? kEpiWarps : 4) * kPatchBytes : 0;   // double-buffered, 1024-byte aligned
+    static_assert(TS == 0 || MODE == 0, "TMA-store epilogue: fprop / dgrad");
+    constexpr int kTsBufs = TS == 2 ? 3 : 2;                                   // patch buffers per epilogue warp
+    constexpr int kTsBufBytes = TS == 3 ? 2 * kPatchBytes : kPatchBytes;       // TS == 2: [operand -> output]; 3: [residual -> output | mask]
+    constexpr int kTsPatchBytes = TS ? kTsBufs * kTsBufBytes * (SPLIT ? EW : 4) : 0;   // 1024-byte aligned region
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes + kTsPatchBytes);
     uint64_t* empty_bar = full_bar + STAGES;
@@ -127,6 +139,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     uint64_t* tmem_full = split_bar + STAGES;                     // [2]
     uint64_t* tmem_empty = tmem_full + 2;                         // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    [[maybe_unused]] uint64_t* ld_bar = tmem_empty + 3;           // TS == 2: [epilogue warp][buffer] residual / mask loads landed
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -168,7 +181,12 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         if (smem_u32(smem) & 1023u) __trap();                     // SWIZZLE_128B tiles need 1024-byte aligned stages
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapB);
-        if constexpr (TS) tma_prefetch_desc(&mapO);
+        if constexpr (TS != 0) tma_prefetch_desc(&mapO);
+        if constexpr (TS >= 2) {
+            tma_prefetch_desc(&mapR);
+            tma_prefetch_desc(&mapM);
+            for (int i = 0; i < 24; ++i) mbar_init(&ld_bar[i], 1);
+        }
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -238,9 +256,9 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         if (elect_one()) {
             constexpr uint32_t idesc = BF ? make_idesc_bf16(BM, BN) : make_idesc_tf32(BM, BN, A_MN && !TA, B_MN);   // A from TMEM is always lane = m, column = k
             constexpr uint64_t kDescHiA = (A_MN ? make_smem_desc(0, kChunkBytes, 512, 1) : make_smem_desc(0, 16, 1024, 2)) & 0xFFFFFFFF00000000ull;
-            constexpr uint64_t kDescHiB = (B_MN ? make_smem_desc(0, kChunkBytes, 512, 1) : make_smem_desc(0, 16, 1024, 2)) & 0xFFFFFFFF00000000ull;
+            constexpr uint64_t kDescHiB = (B_DESC_MN ? make_smem_desc(0, kChunkBytes, 512, 1) : make_smem_desc(0, 16, 1024, 2)) & 0xFFFFFFFF00000000ull;
             constexpr uint32_t kDescLoA = (uint32_t)((A_MN ? make_smem_desc(0, kChunkBytes, 512, 1) : make_smem_desc(0, 16, 1024, 2)) & 0xFFFF0000ull);
-            constexpr uint32_t kDescLoB = (uint32_t)((B_MN ? make_smem_desc(0, kChunkBytes, 512, 1) : make_smem_desc(0, 16, 1024, 2)) & 0xFFFF0000ull);
+            constexpr uint32_t kDescLoB = (uint32_t)((B_DESC_MN ? make_smem_desc(0, kChunkBytes, 512, 1) : make_smem_desc(0, 16, 1024, 2)) & 0xFFFF0000ull);
             const uint32_t smem_base_u32 = smem_u32(smem);
             int git = 0, lt = 0;                                  // lt counts tiles that have a main loop
             for (int tix = blockIdx.x; tix < p.total_tiles; tix += gridDim.x) {
@@ -264,7 +282,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     // MN-major (128B swizzle, 32-B atoms, 4-row period): 8 reduction rows = 1024 B further per k-step;
                     // 4-row groups 512 B apart (SBO); 32-wide MN chunks 4096 B apart (LBO).
                     const uint32_t a_addr = smem_base_u32 + s * kStageBytes;
-                    const uint32_t b_addr = a_addr + kTileABytes;
+                    const uint32_t b_addr = a_addr + kTileABytes + ((BF && MODE == 1) ? kTileBBytes : 0);   // wgrad: the split tile
                     if constexpr (BF) {
                         // bf16x3: k-step = 16 bf16 = 8 TMEM columns of A (two per 32-bit column) / 32 bytes of a B row;
                         // A hi at columns [0,16) of the stage, lo at [16,32); B hi at bytes [0,64) of the row, lo at [64,128).
@@ -318,7 +336,52 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 const int s = git % STAGES;
                 const uint32_t ph = (git / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
-                if constexpr (BF) {
+                if constexpr (BF && MODE == 1) {
+                    // wgrad: both operands arrive MN-major -- chunk (warp & 3) holds 32 channels as [32 reduction rows (pixels)]
+                    // [128 B], 32-byte atoms XOR-swizzled with the row (SWIZZLE_128B_ATOM_32B: atom ^= row & 3).  This thread
+                    // owns dy channel m = its TMEM lane AND x channel n = the same index of the B tile: a warp-wide LDS.32 reads
+                    // one full 128-byte row (conflict-free), 32 of them give the thread its channel's 32 pixels = one K-major
+                    // row, which is split into packed bf16 (hi, lo) pairs: A -> tensor memory, B -> the K-major smem tile.
+                    const int row = (warp & 3) * 32 + lane;
+                    const int atom = lane >> 3;
+                    uint32_t w[32];
+                    {
+                        const uint8_t* acol = smem + s * kStageBytes + (warp & 3) * kChunkBytes + (lane & 7) * 4;
+                        float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float x0 = *reinterpret_cast<const float*>(acol + (2 * j) * 128 + ((atom ^ ((2 * j) & 3)) << 5));
+                            const float x1 = *reinterpret_cast<const float*>(acol + (2 * j + 1) * 128 + ((atom ^ ((2 * j + 1) & 3)) << 5));
+                            q0 += x0; q1 += x1;              // bias gradient for free (TMA zero-fills pixels / channels past the edge)
+                            const uint32_t h = pack_bf16x2(x0, x1);
+                            w[j] = h;
+                            w[16 + j] = pack_bf16x2(x0 - __uint_as_float(h << 16), x1 - __uint_as_float(h & 0xFFFF0000u));
+                        }
+                        rsum += q0 + q1;
+                    }
+                    tmem_st_32x32(tmem_base + 2 * BN + s * kAColsPerStage + ((uint32_t)((warp & 3) * 32) << 16), w);
+                    if (row < BN) {
+                        const uint8_t* bcol = smem + s * kStageBytes + kTileABytes + (warp & 3) * kChunkBytes + (lane & 7) * 4;
+                        uint32_t hw[16], lw[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float x0 = *reinterpret_cast<const float*>(bcol + (2 * j) * 128 + ((atom ^ ((2 * j) & 3)) << 5));
+                            const float x1 = *reinterpret_cast<const float*>(bcol + (2 * j + 1) * 128 + ((atom ^ ((2 * j + 1) & 3)) << 5));
+                            const uint32_t h = pack_bf16x2(x0, x1);
+                            hw[j] = h;
+                            lw[j] = pack_bf16x2(x0 - __uint_as_float(h << 16), x1 - __uint_as_float(h & 0xFFFF0000u));
+                        }
+                        // row n of the K-major tile: 128 bytes = [hi 64 B | lo 64 B], 16-byte chunk c at c ^ (n & 7) (SWIZZLE_128B)
+                        uint8_t* brow = smem + s * kStageBytes + kRawBytes + row * 128;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            *reinterpret_cast<uint4*>(brow + ((c ^ (row & 7)) << 4)) = make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]);
+                            *reinterpret_cast<uint4*>(brow + (((4 + c) ^ (row & 7)) << 4)) = make_uint4(lw[4 * c], lw[4 * c + 1], lw[4 * c + 2], lw[4 * c + 3]);
+                        }
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();             // order the TMEM stores before the MMA thread's reads (pairs with its fence::after)
+                } else if constexpr (BF) {
                     // This thread owns tile row (warp % 4) * 32 + lane = its TMEM lane: 32 fp32 -> 16 packed bf16x2 hi words
                     // (element 2j in the low half) + 16 lo words, lo = bf16(x - float(hi)) (the subtraction is exact).
                     const int row = (warp & 3) * 32 + lane;
@@ -420,7 +483,120 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         // transposed through a private XOR-swizzled smem patch: afterwards 8 lanes x float4 cover one row's 128 bytes and
         // a warp instruction moves 4 full lines -- residual / mask reads use the same coalesced pattern.
         const int q = warp & 3;                // TMEM lane quarter this warp may access
-        if constexpr (TS) {
+        if constexpr (TS >= 2) {
+            // ---- TMA-store epilogue with TMA-loaded residual / mask ---------------------------------------------------
+            // TS == 2: exactly one operand, loaded INTO the output patch; TS == 3: residual there, mask in a second patch.
+            constexpr int kMaskOff = TS == 3 ? kPatchBytes : 0;
+            uint8_t* patches = smem + STAGES * kStageBytes + (warp - kEpiWarp0) * kTsBufs * kTsBufBytes;
+            uint64_t* bars = ld_bar + (warp - kEpiWarp0) * kTsBufs;
+            const int chunk0 = ((warp - kEpiWarp0) >> 2) * 32;
+            constexpr int kChunkStep = 32 * (EPI / 4);
+            const int r0 = q * 32;
+            const int lx0 = r0 % p.tw, lyt0 = r0 / p.tw, ib0 = lyt0 / p.th, ly0 = lyt0 - ib0 * p.th;
+            const uint32_t ld_bytes = (p.residual ? kPatchBytes : 0) + (p.relu_mask ? kPatchBytes : 0);
+            // prefetch iterator: (tile, chunk) of the next operand load, kTsBufs - 1 chunks ahead of the chunk being written
+            int pf_tix = blockIdx.x, pf_c0 = chunk0, n_issued = 0, n = 0;
+            auto pf_norm = [&]() {
+                while (pf_tix < p.total_tiles) {
+                    if (pf_c0 < BN && (pf_tix % p.n_tiles_n) * BN + pf_c0 < p.No) return true;
+                    pf_tix += gridDim.x;
+                    pf_c0 = chunk0;
+                }
+                return false;
+            };
+            auto pf_issue = [&]() {            // lane 0: residual / mask boxes of chunk #n_issued into buffer n_issued % kTsBufs
+                const Tile t = decode(pf_tix);
+                uint8_t* buf = patches + (n_issued % kTsBufs) * kTsBufBytes;
+                uint64_t* bar = &bars[n_issued % kTsBufs];
+                mbar_arrive_expect_tx(bar, ld_bytes);
+                if (p.residual) tma_load_4d(buf, &mapR, bar, t.n0 + pf_c0, t.x0 + lx0, t.y0 + ly0, t.img + ib0);
+                if (p.relu_mask) tma_load_4d(buf + kMaskOff, &mapM, bar, t.n0 + pf_c0, t.x0 + lx0, t.y0 + ly0, t.img + ib0);
+            };
+            bool pf_ok = pf_norm();
+            for (int i = 0; i < kTsBufs - 1 && pf_ok; ++i) {
+                if (lane == 0) pf_issue();
+                ++n_issued;
+                pf_c0 += kChunkStep;
+                pf_ok = pf_norm();
+            }
+            int lt = 0;
+            for (int tix = blockIdx.x; tix < p.total_tiles; tix += gridDim.x) {
+                const Tile t = decode(tix);
+                const int slot = lt & 1;
+                const bool dbg = p.dbg && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0 && lt < 12;
+                if (dbg) p.dbg[lt * 16 + 0] = clock64();
+                if (t.iters > 0) {
+                    mbar_wait(&tmem_full[slot], (lt >> 1) & 1);
+                    tc_fence_after();
+                }
+                if (dbg) p.dbg[lt * 16 + 1] = clock64();
+                const uint32_t taddr_row = tmem_base + slot * BN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+                for (int c0 = chunk0; c0 < BN; c0 += kChunkStep) {
+                    if (t.n0 + c0 >= p.No) break;  // uniform across the warp
+                    // operands of chunk n + kTsBufs - 1 go into the buffer chunk n - 1 used: its bulk store must be done reading
+                    if (pf_ok) {
+                        if (lane == 0) {
+                            tma_store_wait_read<0>();
+                            pf_issue();
+                        }
+                        ++n_issued;
+                        pf_c0 += kChunkStep;
+                        pf_ok = pf_norm();
+                    }
+                    uint8_t* buf = patches + (n % kTsBufs) * kTsBufBytes;
+                    uint32_t r[32];
+                    if (t.iters > 0) {
+                        tmem_ld_32x32(taddr_row + c0, r);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = 0u;
+                    }
+                    float4 b4[8];
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            b4[j] = (t.n0 + c0 + 4 * j < p.No) ? __ldg(reinterpret_cast<const float4*>(p.bias + t.n0 + c0) + j)
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    mbar_wait(&bars[n % kTsBufs], (n / kTsBufs) & 1);     // residual / mask boxes of this chunk have landed
+                    if (t.iters > 0) tmem_ld_wait();
+                    if (dbg && c0 < 128) p.dbg[lt * 16 + 2 + (c0 >> 5) * 3] = clock64();
+                    uint8_t* prow = buf + lane * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4* slot4 = reinterpret_cast<float4*>(prow + ((j ^ (lane & 7)) << 4));
+                        float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                               __uint_as_float(r[4 * j + 3]));
+                        if (p.bias) { v.x += b4[j].x; v.y += b4[j].y; v.z += b4[j].z; v.w += b4[j].w; }
+                        if (p.residual) { const float4 e = *slot4; v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w; }
+                        if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        if (p.relu_mask) {
+                            const float4 m4 = *reinterpret_cast<const float4*>(prow + kMaskOff + ((j ^ (lane & 7)) << 4));
+                            v.x = m4.x > 0.f ? v.x : 0.f; v.y = m4.y > 0.f ? v.y : 0.f;
+                            v.z = m4.z > 0.f ? v.z : 0.f; v.w = m4.w > 0.f ? v.w : 0.f;
+                        }
+                        *slot4 = v;
+                    }
+                    fence_proxy_async_smem();      // generic-proxy accesses before the TMA unit's reads (store) and later writes (loads)
+                    __syncwarp();
+                    if (dbg && c0 < 128) p.dbg[lt * 16 + 3 + (c0 >> 5) * 3] = clock64();
+                    if (lane == 0) {
+                        tma_store_4d(&mapO, buf, t.n0 + c0, t.x0 + lx0, t.y0 + ly0, t.img + ib0);
+                        tma_store_commit();
+                    }
+                    if (dbg && c0 < 128) p.dbg[lt * 16 + 4 + (c0 >> 5) * 3] = clock64();
+                    ++n;
+                }
+                if (t.iters > 0) {
+                    tc_fence_before();             // TMEM reads of this warp are done: hand the accumulator back
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[slot]);
+                    ++lt;
+                }
+            }
+            if (lane == 0) tma_store_wait_all();
+        } else if constexpr (TS == 1) {
             // ---- TMA-store epilogue ----------------------------------------------------------------------------------
             uint8_t* patches = smem + STAGES * kStageBytes + (warp - kEpiWarp0) * 2 * kPatchBytes;
             const int chunk0 = ((warp - kEpiWarp0) >> 2) * 32;
@@ -489,7 +665,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             }
             if (lane == 0) tma_store_wait_all();   // every bulk store of this warp has been written out before the CTA exits
         } else {
-        float* patch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256) + (warp - kEpiWarp0) * (32 * 32);
+        float* patch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 512) + (warp - kEpiWarp0) * (32 * 32);
         const int chunk0 = ((warp - kEpiWarp0) >> 2) * 32;       // EPI == 8: warps 4..7 take the odd 32-column chunks
         const int r4 = lane >> 3, c4 = lane & 7;
         int lt = 0;
@@ -731,15 +907,17 @@ int num_sms_tc() {
 
 // `grid` carries the logical tile counts (x = column tiles, y = row tiles, z = split-K slices); the kernel is
 // launched persistent with min(total_tiles, SMs * resident CTAs) CTAs.
-template <int BN, int STAGES, int MODE, bool B_MN, bool SPLIT, bool TA = false, bool BF = false, bool TS = false>
-int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, dim3 grid, cudaStream_t stream, const CUtensorMap* o = nullptr) {
-    constexpr int stage = BF ? kTileABytes + BN * 128 : (TA ? kTileABytes + 2 * BN * 128 : (SPLIT ? 2 : 1) * (kTileABytes + BN * 128));
-    constexpr int smem = STAGES * stage + 1024 /*align slack*/ + 256 /*barriers*/ + (TS ? 2 : 1) * (SPLIT ? kEpiWarps : 4) * kPatchBytes;
+template <int BN, int STAGES, int MODE, bool B_MN, bool SPLIT, bool TA = false, bool BF = false, int TS = 0, int EW = kEpiWarps>
+int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, dim3 grid, cudaStream_t stream, const CUtensorMap* o = nullptr,
+              const CUtensorMap* r = nullptr, const CUtensorMap* m = nullptr) {
+    constexpr int stage = BF ? kTileABytes + (MODE == 1 ? 2 : 1) * BN * 128 : (TA ? kTileABytes + 2 * BN * 128 : (SPLIT ? 2 : 1) * (kTileABytes + BN * 128));
+    constexpr int smem = STAGES * stage + 1024 /*align slack*/ + 512 /*barriers*/ +
+                         (TS == 3 ? 4 : (TS == 2 ? 3 : (TS == 1 ? 2 : 1))) * (SPLIT ? EW : 4) * kPatchBytes;
     static_assert(smem <= 227 * 1024, "dynamic shared memory budget");
-    constexpr int threads = SPLIT ? 192 + 32 * kEpiWarps : 192;
+    constexpr int threads = SPLIT ? 192 + 32 * EW : 192;
     static bool configured[kMaxDevices] = {};                     // the attribute is per (function, device)
-    auto kern = tc_conv_gemm_kernel<BN, STAGES, MODE, B_MN, SPLIT, TA, BF, TS>;
-    if (TS && !o) return MDB_EINVAL;
+    auto kern = tc_conv_gemm_kernel<BN, STAGES, MODE, B_MN, SPLIT, TA, BF, TS, EW>;
+    if (TS != 0 && !o) return MDB_EINVAL;
     const int dev = current_device();
     if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -753,7 +931,7 @@ int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, dim3 grid,
     int ctas = num_sms_tc() * resident;
     if (ctas > p.total_tiles) ctas = p.total_tiles;
     if (ctas < 1) return 0;
-    kern<<<ctas, threads, smem, stream>>>(a, b, o ? *o : a, p);
+    kern<<<ctas, threads, smem, stream>>>(a, b, o ? *o : a, r ? *r : a, m ? *m : a, p);
     return (int)cudaGetLastError();
 }
 
@@ -807,20 +985,55 @@ void pick_tile3(int W, int H, int B, int n_pix, int* tw, int* th, int* tb) {
         }
 }
 
-// Output tensor map of the TMA-store epilogue (TS kernels): out as (No, W, H, images) with one epilogue warp's 32-row slice
-// of the tw x th x tb tile as the box.  Returns false when the register epilogue has to be used instead.
-bool make_out_map(CUtensorMap* mo, const TcParams& p) {
-    static const bool enabled = getenv("MDB_NO_TMA_STORE") == nullptr;            // A/B switch (profiling)
-    if (!enabled || p.residual || p.relu_mask || p.atomic_out || p.kb_per_slice > 0 || p.round_out) return false;
-    if (p.out_sx != 1 || p.out_sy != 1 || p.out_ox != 0 || p.out_oy != 0 || (p.ldo & 3) || p.No != p.ldo) return false;
-    if ((reinterpret_cast<uintptr_t>(p.out) & 15u) || (p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15u))) return false;
+// Tensor maps of the TMA-store epilogues (TS kernels): out -- and the residual / ReLU-mask operands, which are indexed like
+// out -- as (No, W, H, images) with one epilogue warp's 32-row slice of the tw x th x tb tile as the box.  Returns the
+// epilogue variant: 0 = register epilogue (strided / ragged / atomic / split-K outputs), 1 = TMA store, 2 = TMA store with
+// one TMA-loaded operand (residual or mask), 3 = with both.
+int make_epilogue_maps(CUtensorMap* mo, CUtensorMap* mr, CUtensorMap* mm, const TcParams& p) {
+    static const bool enabled = getenv("MDB_NO_TMA_STORE") == nullptr;            // A/B switches (profiling)
+    static const bool enabled2 = getenv("MDB_NO_TMA_EPILOGUE_LOADS") == nullptr;
+    const bool operands = p.residual || p.relu_mask;
+    if (!enabled || (operands && !enabled2) || p.atomic_out || p.kb_per_slice > 0 || p.round_out) return 0;
+    if (p.out_sx != 1 || p.out_sy != 1 || p.out_ox != 0 || p.out_oy != 0 || (p.ldo & 3) || p.No != p.ldo) return 0;
+    if ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.bias) | reinterpret_cast<uintptr_t>(p.residual) |
+         reinterpret_cast<uintptr_t>(p.relu_mask)) & 15u)
+        return 0;
     const int bw = p.tw < 32 ? p.tw : 32;
     const int bh = p.th < 32 / bw ? p.th : 32 / bw;
     const int bb = 32 / (bw * bh);
     uint64_t dims[4] = {(uint64_t)p.No, (uint64_t)p.out_W, (uint64_t)p.out_H, (uint64_t)p.n_img};
     uint64_t str[4] = {1, (uint64_t)p.ldo, (uint64_t)p.out_W * p.ldo, (uint64_t)p.out_H * p.out_W * p.ldo};
     uint32_t box[4] = {32, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
-    return make_map(mo, p.out, 4, dims, str, box, nullptr) == 0;
+    if (make_map(mo, p.out, 4, dims, str, box, nullptr) != 0) return 0;
+    if (p.residual && make_map(mr, p.residual, 4, dims, str, box, nullptr) != 0) return 0;
+    if (p.relu_mask && make_map(mm, p.relu_mask, 4, dims, str, box, nullptr) != 0) return 0;
+    return (p.residual && p.relu_mask) ? 3 : (operands ? 2 : 1);
+}
+
+// Launch the bf16x3 fprop / dgrad kernel with the epilogue variant the output allows.
+int launch_bf(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, int bn, cudaStream_t stream) {
+    CUtensorMap mo, mr, mm;
+    const int ts = make_epilogue_maps(&mo, &mr, &mm, p);
+    const CUtensorMap* r = p.residual ? &mr : nullptr;
+    const CUtensorMap* m = p.relu_mask ? &mm : nullptr;
+    static const bool ew8 = getenv("MDB_EPI_WARPS_4") == nullptr;                 // A/B switch (profiling)
+    if (ew8) {   // 8 epilogue warps; stages sized so that ring + patches fill the 227 KB
+        if (ts == 3) return bn == 64 ? launch_tc<64, 4, 0, false, true, true, true, 3, 8>(ma, mb, p, grid, stream, &mo, r, m)
+                                     : launch_tc<128, 3, 0, false, true, true, true, 3, 8>(ma, mb, p, grid, stream, &mo, r, m);
+        if (ts == 2) return bn == 64 ? launch_tc<64, 5, 0, false, true, true, true, 2, 8>(ma, mb, p, grid, stream, &mo, r, m)
+                                     : launch_tc<128, 4, 0, false, true, true, true, 2, 8>(ma, mb, p, grid, stream, &mo, r, m);
+        if (ts == 1) return bn == 64 ? launch_tc<64, 6, 0, false, true, true, true, 1, 8>(ma, mb, p, grid, stream, &mo)
+                                     : launch_tc<128, 5, 0, false, true, true, true, 1, 8>(ma, mb, p, grid, stream, &mo);
+    } else {
+        if (ts == 3) return bn == 64 ? launch_tc<64, 6, 0, false, true, true, true, 3, 4>(ma, mb, p, grid, stream, &mo, r, m)
+                                     : launch_tc<128, 5, 0, false, true, true, true, 3, 4>(ma, mb, p, grid, stream, &mo, r, m);
+        if (ts == 2) return bn == 64 ? launch_tc<64, 6, 0, false, true, true, true, 2, 4>(ma, mb, p, grid, stream, &mo, r, m)
+                                     : launch_tc<128, 5, 0, false, true, true, true, 2, 4>(ma, mb, p, grid, stream, &mo, r, m);
+        if (ts == 1) return bn == 64 ? launch_tc<64, 8, 0, false, true, true, true, 1, 4>(ma, mb, p, grid, stream, &mo)
+                                     : launch_tc<128, 6, 0, false, true, true, true, 1, 4>(ma, mb, p, grid, stream, &mo);
+    }
+    return bn == 64 ? launch_tc<64, 8, 0, false, true, true, true>(ma, mb, p, grid, stream)
+                    : launch_tc<128, 6, 0, false, true, true, true>(ma, mb, p, grid, stream);
 }
 
 struct ConvGeom {
@@ -964,14 +1177,7 @@ int conv_forward_impl(const float* x, const void* w_packed, bool bf, const float
             return (int)cudaGetLastError();
         }
     }
-    if (bf) {
-        CUtensorMap mo;
-        if (make_out_map(&mo, p))
-            return bn == 64 ? launch_tc<64, 8, 0, false, true, true, true, true>(ma, mb, p, grid, stream, &mo)
-                            : launch_tc<128, 6, 0, false, true, true, true, true>(ma, mb, p, grid, stream, &mo);
-        return bn == 64 ? launch_tc<64, 8, 0, false, true, true, true>(ma, mb, p, grid, stream)
-                        : launch_tc<128, 6, 0, false, true, true, true>(ma, mb, p, grid, stream);
-    }
+    if (bf) return launch_bf(ma, mb, p, grid, bn, stream);
     if (bn == 64) return (precision == 1) ? (tmem_a ? launch_tc<64, 6, 0, false, true, true>(ma, mb, p, grid, stream)
                                                     : launch_tc<64, 4, 0, false, true>(ma, mb, p, grid, stream))
                                           : launch_tc<64, 6, 0, false, false>(ma, mb, p, grid, stream);
@@ -1060,12 +1266,7 @@ int conv_dgrad_impl(const float* dy, const void* w_packed, bool bf, const float*
                 p.ntaps = 0;
             }
             static const bool tmem_a = getenv("MDB_NO_TMEM_A") == nullptr;
-            CUtensorMap mo;
-            if (bf && make_out_map(&mo, p))
-                rc = bn == 64 ? launch_tc<64, 8, 0, false, true, true, true, true>(ma, mb, p, grid, stream, &mo)
-                              : launch_tc<128, 6, 0, false, true, true, true, true>(ma, mb, p, grid, stream, &mo);
-            else if (bf) rc = bn == 64 ? launch_tc<64, 8, 0, false, true, true, true>(ma, mb, p, grid, stream)
-                                       : launch_tc<128, 6, 0, false, true, true, true>(ma, mb, p, grid, stream);
+            if (bf) rc = launch_bf(ma, mb, p, grid, bn, stream);
             else rc = (precision == 1) ? (tmem_a ? launch_tc<128, 4, 0, true, true, true>(ma, mb, p, grid, stream)
                                                  : launch_tc<128, 3, 0, true, true>(ma, mb, p, grid, stream))
                                        : launch_tc<128, 5, 0, true, false>(ma, mb, p, grid, stream);
@@ -1193,6 +1394,8 @@ int mdb_conv2d_wgrad_bias_f32(const float* dy, const float* x, const float* rows
         if (rc) return rc;
     }
     dim3 grid((Cin + bn - 1) / bn, (Cout + BM - 1) / BM, taps * splits);
+    static const bool bf_wgrad = getenv("MDB_NO_BF16_WGRAD") == nullptr;         // A/B switch (profiling)
+    if (g_precision == 2 && bf_wgrad) return launch_tc<128, 4, 1, true, true, true, true>(ma, mb, p, grid, stream);
     rc = (g_precision != 0) ? (tmem_a ? launch_tc<128, 4, 1, true, true, true>(ma, mb, p, grid, stream)
                                       : launch_tc<128, 3, 1, true, true>(ma, mb, p, grid, stream))
          : (bn == 256)      ? launch_tc<256, 4, 1, true, false>(ma, mb, p, grid, stream)
