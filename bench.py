@@ -359,6 +359,14 @@ def main():
         from monodetr_b200 import bench_model
         line = bench_model.run(args, rank, local_rank, ws, infer=(args.workload == "infer"))
         if line is not None and ws == 1 and args.workload == "model":
+            if not args.batch and not os.environ.get("MDB_BENCH_NO_B16"):
+                # the N > 1 runs use batch 16 per GPU (BASELINE configs[3]): the like-for-like single-GPU point for scaling
+                import gc
+                gc.collect(); torch.cuda.empty_cache()
+                b16 = bench_model.run(args, rank, local_rank, ws, batch_override=16, extras=False)
+                line["batch16"] = {"value": b16["value"], "unit": "images/sec", "ms_per_step": b16["ms_per_step"],
+                                   "e2e": b16["e2e"]["value"], "note": "same step at batch 16/GPU (the per-GPU batch of the N>1 runs): "
+                                   "use this value, not `value`, as the 1-GPU point of a like-for-like scaling efficiency"}
             line["cpu_baseline"] = cpu_baseline_model()
     if line is not None:
         print(json.dumps(line), flush=True)

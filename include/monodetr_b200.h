@@ -56,12 +56,6 @@ int mdb_msda_backward_f32(const float* value, const int64_t* spatial_shapes, con
                           const float* sampling_loc, const float* attn_weight, const float* grad_out,
                           int B, int S, int M, int D, int L, int Lq, int P,
                           float* grad_value, float* grad_loc, float* grad_attn, void* stream);
-/* Same, with a HOST copy of spatial_shapes (L x 2 int64; same values as the device tensor): lets the launcher size the
- * shared-memory accumulators of the encoder-sized fast path (coarse levels privatised per CTA); NULL = mdb_msda_backward_f32. */
-int mdb_msda_backward_hs_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
-                             const int64_t* host_spatial_shapes, const float* sampling_loc, const float* attn_weight,
-                             const float* grad_out, int B, int S, int M, int D, int L, int Lq, int P,
-                             float* grad_value, float* grad_loc, float* grad_attn, void* stream);
 int mdb_msda_backward_f64(const double* value, const int64_t* spatial_shapes, const int64_t* level_start,
                           const double* sampling_loc, const double* attn_weight, const double* grad_out,
                           int B, int S, int M, int D, int L, int Lq, int P,
@@ -92,11 +86,11 @@ int mdb_msda_prep_backward_f32(const float* dloc, const float* dattn, const floa
  * >= 256 k-blocks and few tiles (3x3 stride-2 2048->256, monodetr.py:83-91) reduces through the scratch buffer the caller
  * registers with mdb_set_workspace (per device; the library itself never allocates or frees device memory).
  */
-/* Arithmetic of the tensor-core family (a process-wide numerical setting): 1 = error-compensated 3xTF32 (A*B + A_lo*B +
- * A*B_lo, ~fp32 accuracy); 0 = single-pass TF32 with round-to-nearest operands (cuDNN's allow_tf32 class); 2 = error-
- * compensated BF16x3 for forward / dgrad (operands split into bf16 hi + lo, same three products at twice the tensor rate,
- * relative error ~2^-17 per product; weights arrive pre-split through mdb_pack_gemm_weights_bf16x3 and the *_bf16x3 entry
- * points; the _f32 entry points and wgrad run 3xTF32 in this mode). */
+/* Arithmetic of the tensor-core family (a process-wide numerical setting): 2 (default) = error-compensated BF16x3 (operands
+ * split into bf16 hi + lo, A_hi*B_hi + A_lo*B_hi + A_hi*B_lo at twice the TF32 tensor rate, dropped terms ~2^-17 per product;
+ * forward / dgrad take pre-split weights through mdb_pack_gemm_weights_bf16x3 and the *_bf16x3 entry points, wgrad splits both
+ * activations on the fly; the _f32 forward / dgrad entry points run 3xTF32 in this mode); 1 = error-compensated 3xTF32
+ * (A*B + A_lo*B + A*B_lo, ~fp32 accuracy); 0 = single-pass TF32 with round-to-nearest operands (cuDNN's allow_tf32 class). */
 int mdb_set_precision(int mode);
 int mdb_get_precision(void);
 /* Split-K scratch of mdb_conv2d_forward_* for the CURRENT device (cudaGetDevice): the library never allocates device

@@ -62,13 +62,45 @@ class MsdaProbe:
         return statistics.mean(ts) if ts else None
 
 
-def run(args, rank, local_rank, ws, infer=False):
+def gemm_probe(dev, flush):
+    """`roofline_gemm`: the dominant kernel family (tc_conv_gemm_kernel: ~50 % of the step) timed alone with CUDA events on
+    the three shapes that carry most of its FLOPs at batch 8 -- a ResNet 3x3 convolution (layer3), the encoder-sized linear
+    (M = 81 600, N = K = 256: value_proj / output_proj / FFN of the three encoder layers) forward, and that linear's weight
+    gradient.  Useful FLOPs (2 M N K, one product per MAC although the bf16x3 arithmetic issues three) / launch time."""
+    g = torch.Generator(device=dev).manual_seed(0)
+    out = []
+    x = torch.randn(8, 24, 80, 256, device=dev, generator=g)
+    w = torch.randn(256, 256, 3, 3, device=dev, generator=g) / 48.0
+    xl = torch.randn(81600, 256, device=dev, generator=g)
+    wl = torch.randn(256, 256, device=dev, generator=g) / 16.0
+    dyl = torch.randn(81600, 256, device=dev, generator=g)
+    sw = tc.split_weights([w])[0] if tc.get_precision() == "bf16x3" else tc.pack_weight(w)
+    swl = tc.split_weights([wl])[0] if tc.get_precision() == "bf16x3" else wl
+    cases = [("conv3x3 256->256 @ 8x24x80 fwd", 2.0 * 8 * 24 * 80 * 256 * 256 * 9, lambda: tc.conv2d_forward(x, sw, None, None, 3, 3, 1, 1)),
+             ("linear 81600x256x256 fwd", 2.0 * 81600 * 256 * 256, lambda: tc.linear_forward(xl, swl)),
+             ("linear 81600x256x256 wgrad", 2.0 * 81600 * 256 * 256, lambda: tc.linear_wgrad(dyl, xl))]
+    for name, flops, fn in cases:
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = statistics.mean(ts)
+        out.append({"shape": name, "avg_ms": ms, "tflops": flops / (ms * 1e-3) / 1e12})
+    return out
+
+
+def run(args, rank, local_rank, ws, infer=False, batch_override=None, extras=True):
     """infer=False: BASELINE configs[2]/[3] (train step).  infer=True: configs[4], eval-mode forward only, batch 32,
     no gradients, N>1 = independent replicas (no collective)."""
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-    B = args.batch or (32 if infer else (8 if ws == 1 else 16))
-    precision = os.environ.get("MDB_PRECISION", "tf32x3")
+    B = batch_override or args.batch or (32 if infer else (8 if ws == 1 else 16))
+    precision = os.environ.get("MDB_PRECISION", "bf16x3")
     tc.set_precision(precision)
     torch.manual_seed(0)
     model, _ = build_monodetr(DEFAULT_MODEL_CFG)
@@ -159,6 +191,20 @@ def run(args, rank, local_rank, ws, infer=False):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_ms = float(tt.item())
 
+    # ---- exposed all-reduce (N > 1): the flat-bucket pack + ncclAllReduce + divide run after the graph replay, not overlapped
+    allreduce_ms = None
+    if bucket is not None and ws > 1:
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            bucket.all_reduce()
+        a1.record()
+        barrier()
+        ta = torch.tensor([a0.elapsed_time(a1) / args.steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        allreduce_ms = float(ta.item())
+
     # ---- end to end through the public API with HOST inputs: H2D of the batch + D2H of the loss every step ------
     # Input feeding is double-buffered the way a data loader would do it: a copy stream moves batch i+1 from pinned host
     # memory into a staging buffer while step i runs; the step's own stream waits for the copy, takes the batch with a
@@ -204,12 +250,15 @@ def run(args, rank, local_rank, ws, infer=False):
     h2d = sum(t.numel() * t.element_size() for t in host)
 
     # ---- MSDA kernel duration in situ (eager steps, events around the launches; real sampling locations) --------
-    with MsdaProbe() as probe:
-        for _ in range(3):
-            fwd_bwd()
-        torch.cuda.synchronize()
-        enc_ms = probe.encoder_ms()
+    enc_ms = None
+    if extras:
+        with MsdaProbe() as probe:
+            for _ in range(3):
+                fwd_bwd()
+            torch.cuda.synchronize()
+            enc_ms = probe.encoder_ms()
     loss_val = float(loss_buf.item())
+    gemm = gemm_probe(dev, flush) if (extras and rank == 0 and not infer) else None
 
     if rank != 0:
         return None
@@ -230,7 +279,8 @@ def run(args, rank, local_rank, ws, infer=False):
                                   "bf16x3": "error-compensated BF16x3 (hi/lo split operands, fp32 accumulate) for forward and data-gradient GEMMs, 3xTF32 weight-gradient GEMMs"}[precision],
                    "parallelism": f"dp{ws}", "global_batch": B * ws,
                    "timing": "CUDA events per step; 256 MiB L2 flush (untimed) between steps; " + ("CUDA graph replay" if graph is not None else "eager launches")
-                             + "; e2e: batch double-buffered from pinned host memory on a copy stream, every step's H2D + loss D2H inside the timed region"},
+                             + "; e2e: batch double-buffered from pinned host memory on a copy stream, every step's H2D + loss D2H inside the timed "
+                               "region, NO L2 flush between its steps (which is why e2e can exceed `value` by the cold-L2 penalty of a step)"},
         "e2e": {"value": B * ws * args.steps / (e2e_ms * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
@@ -238,6 +288,15 @@ def run(args, rank, local_rank, ws, infer=False):
         "model_tflops": flops_img * B / (ms_step * 1e-3) / 1e12,
         "tensor_frac_of_measured_bf16_peak": flops_img * B / (ms_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
     }
+    if allreduce_ms is not None:
+        line["allreduce_ms_exposed"] = allreduce_ms
+    if gemm:
+        best = max(gemm, key=lambda c: c["tflops"])
+        line["roofline_gemm"] = {"kernel": "tc_conv_gemm_kernel (tcgen05 BF16x3 implicit GEMM; " + best["shape"] + ")", "bound": "tensor",
+                                 "achieved": best["tflops"], "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": best["tflops"] / pk["bf16_tflops"],
+                                 "traffic": None, "peak_source": pk["source"] + " (burst: kernel timed alone)",
+                                 "note": "useful FLOPs; the error-compensated arithmetic issues 3 tensor-core products per MAC, so 1/3 is the ceiling of this ratio",
+                                 "shapes": gemm}
     if enc_ms:
         ach = fwd_bytes / (enc_ms * 1e-3) / 1e9
         line["roofline"] = {"kernel": "msda_fwd_d32_kernel (encoder call, Lq=10200, in situ)", "bound": "hbm", "achieved": ach,

@@ -186,13 +186,13 @@ __device__ __forceinline__ DropCtx make_drop(const AttnParams& p, int b, int h) 
     DropCtx d;
     d.on = p.drop_p > 0.f;
     d.inv_keep = 1.f / (1.f - p.drop_p);
-    d.thr = (uint32_t)fminf(p.drop_p * 4294967296.f, 4294967040.f);
+    d.thr = mdb::rng_thr16(p.drop_p);
     d.key = 0u;
     if (d.on) d.key = mdb::rng_key32(*p.seed + p.site * 0x9E3779B97F4A7C15ull, (unsigned long long)(b * p.H + h));
     return d;
 }
 __device__ __forceinline__ float keep_scale(const DropCtx& d, uint32_t row_base, int j) {   // row_base = i * Lk
-    return mdb::rng_keep32(d.key, row_base + (uint32_t)j, d.thr) ? d.inv_keep : 0.f;
+    return mdb::rng_keep16(d.key, row_base + (uint32_t)j, d.thr) ? d.inv_keep : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -511,6 +511,17 @@ int check(const AttnParams& p) {
 
 }  // namespace
 
+// attention_tc.cu: tcgen05 / TMEM forward for long key sequences (MDB_EUNSUPPORTED = not applicable, use the kernel below)
+int mdb_attention_forward_tc(const float* q, const float* k, const float* v, const unsigned char* key_padding_mask, float* out,
+                             float* lse, int B, int H, int Lq, int Lk, int ldq, int ldk, int ldv, int ldo, float drop_p,
+                             const unsigned long long* seed, unsigned long long site, cudaStream_t stream);
+
+// attention_tc_bwd.cu: tcgen05 / TMEM backward (dQ and dK/dV kernels) for long key sequences
+int mdb_attention_backward_tc(const float* q, const float* k, const float* v, const unsigned char* key_padding_mask, const float* lse,
+                              const float* dout, const float* delta, float* dq, float* dk, float* dv, int B, int H, int Lq, int Lk,
+                              int ldq, int ldk, int ldv, int ldo, int lddq, int lddk, int lddv, float drop_p,
+                              const unsigned long long* seed, unsigned long long site, cudaStream_t stream);
+
 extern "C" {
 
 int mdb_attention_forward_f32(const float* q, const float* k, const float* v, const unsigned char* key_padding_mask,
@@ -525,6 +536,9 @@ int mdb_attention_forward_f32(const float* q, const float* k, const float* v, co
     p.scale = 1.f / sqrtf((float)HD); p.drop_p = drop_p; p.seed = seed; p.site = site;
     int rc = check(p);
     if (rc) return rc;
+    rc = mdb_attention_forward_tc(q, k, v, key_padding_mask, out, lse, B, H, Lq, Lk, ldq, ldk, ldv, ldo, drop_p, seed, site,
+                                  static_cast<cudaStream_t>(stream));
+    if (rc != MDB_EUNSUPPORTED) return rc;                          // ran (0) or failed: either way not the register kernel's call
     dim3 grid((Lq + BR - 1) / BR, H, B);
     constexpr int kFwdSmem = 4 * BC * LDS * 4 + 2 * STG * 4 + BC;
     static bool attr_set[64] = {};                 // the attribute is per (function, device): several devices per process
@@ -558,6 +572,9 @@ int mdb_attention_backward_f32(const float* q, const float* k, const float* v, c
     if ((lddq | lddk | lddv) % 4) return MDB_EINVAL;
     const long long n = (long long)B * Lq * H;
     attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p);
+    rc = mdb_attention_backward_tc(q, k, v, key_padding_mask, lse, dout, delta_ws, dq, dk, dv, B, H, Lq, Lk, ldq, ldk, ldv, ldo, lddq,
+                                   lddk, lddv, drop_p, seed, site, stream);
+    if (rc != MDB_EUNSUPPORTED) return rc;
     attn_bwd_dq_kernel<<<dim3((Lq + BR - 1) / BR, H, B), ATT_THREADS, 0, stream>>>(p);
     attn_bwd_dkv_kernel<<<dim3((Lk + BR - 1) / BR, H, B), ATT_THREADS, 0, stream>>>(p);
     return (int)cudaGetLastError();

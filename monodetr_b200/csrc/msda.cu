@@ -375,147 +375,6 @@ msda_bwd_vec_kernel(const float* __restrict__ value, const int64_t* __restrict__
 
 
 // ------------------------------------------------------------------------------------------------
-// Backward with the COARSE levels' value gradients privatised in shared memory (D = 32, L = 4, P = 4; encoder-sized Lq).
-// The plain kernel above sends every corner of every sample point to L2 as a 128-byte vector reduction; half of the
-// points fall on the two coarse levels, whose 600 pixels (1280x384 input) absorb 50 % of all reductions -- heavy
-// same-line contention in the L2 atomic units, which is what bounds the kernel (profiles/r01_msda_bwd_model_r1.txt).
-// Here a CTA works on ONE (image, head) pair and a contiguous slice of its queries: the gradient rows of levels
-// >= `lpriv` for that pair (pixels x 32 floats) live in shared memory, are accumulated with shared-memory atomics and are
-// flushed ONCE per CTA with vector reductions (several CTAs may share a pair); the fine levels keep red.global.add.v4.
-// Sample math and grad_loc / grad_attn are identical to msda_bwd_vec_kernel<8, 4> (same instruction order).
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2)
-msda_bwd_priv_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi,
-                     const float* __restrict__ loc, const float* __restrict__ attn, const float* __restrict__ grad_out,
-                     int S, int M, int Lq, int split, int q_per_part, int lpriv, int priv_start, int priv_pixels,
-                     float* __restrict__ grad_value, float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
-    constexpr int L = 4, P = 4, LPU = 8, D = 32, UPW = 4;
-    constexpr int NLOC = 2 * L * P, NV = 3 * L * P, PER = NV / LPU;
-    extern __shared__ __align__(16) float gacc[];                 // [priv_pixels][32]
-    __shared__ LevelInfo lv;
-    if (threadIdx.x < L) {
-        lv.H[threadIdx.x] = (int)shapes[2 * threadIdx.x];
-        lv.W[threadIdx.x] = (int)shapes[2 * threadIdx.x + 1];
-        lv.start[threadIdx.x] = (int)lsi[threadIdx.x];
-    }
-    for (int i = threadIdx.x; i < priv_pixels * (D / 4); i += kThreads) reinterpret_cast<float4*>(gacc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31;
-    const int sub = lane / LPU, cl = lane % LPU;
-    const int wib = threadIdx.x >> 5;
-    const int pix = M * D;
-    const int pair = blockIdx.x / split, part = blockIdx.x - pair * split;
-    const int b = pair / M, m = pair - b * M;
-    const int q_begin = part * q_per_part;
-    const int q_end = min(Lq, q_begin + q_per_part);
-    const int q_end_pad = q_begin + ((q_end - q_begin + UPW - 1) / UPW) * UPW;    // warps stay converged for the shuffles
-    const size_t vbase = ((size_t)b * S * M + m) * D + cl * 4;
-
-    for (int q = q_begin + wib * UPW + sub; q < q_end_pad; q += (kThreads / 32) * UPW) {
-        const bool live = q < q_end;
-        const size_t u = ((size_t)b * Lq + (live ? q : q_begin)) * M + m;
-        const float* lp = loc + u * L * P * 2;
-        const float* ap = attn + u * L * P;
-        float4 g = ldg4(grad_out + u * D + cl * 4);
-        if (!live) g = make_float4(0.f, 0.f, 0.f, 0.f);
-        float vals[NV];
-#pragma unroll
-        for (int l = 0; l < L; ++l) {
-            const int H = lv.H[l], W = lv.W[l];
-            const size_t lbase = vbase + (size_t)lv.start[l] * pix;
-            const bool priv = l >= lpriv;                          // uniform
-            const int sbase = (lv.start[l] - priv_start) * D + cl * 4;
-            const float4 xy01 = ldg4(lp + l * 8);
-            const float4 xy23 = ldg4(lp + l * 8 + 4);
-            const float4 a4 = ldg4(ap + l * 4);
-            const float xs[4] = {xy01.x, xy01.z, xy23.x, xy23.z};
-            const float ys[4] = {xy01.y, xy01.w, xy23.y, xy23.w};
-            const float as[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                const float x = fmaf(xs[p], (float)W, -0.5f);
-                const float y = fmaf(ys[p], (float)H, -0.5f);
-                const bool inside = live && (y > -1.f) && (x > -1.f) && (y < (float)H) && (x < (float)W);
-                const float xf = floorf(x), yf = floorf(y);
-                const int x0 = (int)xf, y0 = (int)yf;
-                const float lx = x - xf, ly = y - yf, hx = 1.f - lx, hy = 1.f - ly;
-                const bool top = inside && (y0 >= 0), bot = inside && (y0 + 1 <= H - 1);
-                const bool lef = (x0 >= 0), rig = (x0 + 1 <= W - 1);
-                const int pidx = y0 * W + x0;
-                const long long o00 = (long long)lbase + (long long)pidx * pix;
-                const long long o01 = o00 + pix, o10 = o00 + (long long)W * pix, o11 = o10 + pix;
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 v1 = (top && lef) ? ldg4(value + o00) : z;
-                const float4 v2 = (top && rig) ? ldg4(value + o01) : z;
-                const float4 v3 = (bot && lef) ? ldg4(value + o10) : z;
-                const float4 v4 = (bot && rig) ? ldg4(value + o11) : z;
-                const float a = as[p];
-                const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-                const float tx = g.x * a, ty = g.y * a, tz = g.z * a, tw = g.w * a;
-                if (priv) {
-                    float* s00 = gacc + sbase + pidx * D;
-                    if (top && lef) { atomicAdd(s00, w1 * tx); atomicAdd(s00 + 1, w1 * ty); atomicAdd(s00 + 2, w1 * tz); atomicAdd(s00 + 3, w1 * tw); }
-                    if (top && rig) { float* s = s00 + D; atomicAdd(s, w2 * tx); atomicAdd(s + 1, w2 * ty); atomicAdd(s + 2, w2 * tz); atomicAdd(s + 3, w2 * tw); }
-                    if (bot && lef) { float* s = s00 + W * D; atomicAdd(s, w3 * tx); atomicAdd(s + 1, w3 * ty); atomicAdd(s + 2, w3 * tz); atomicAdd(s + 3, w3 * tw); }
-                    if (bot && rig) { float* s = s00 + W * D + D; atomicAdd(s, w4 * tx); atomicAdd(s + 1, w4 * ty); atomicAdd(s + 2, w4 * tz); atomicAdd(s + 3, w4 * tw); }
-                } else {
-                    if (top && lef) red_add_v4(grad_value + o00, w1 * tx, w1 * ty, w1 * tz, w1 * tw);
-                    if (top && rig) red_add_v4(grad_value + o01, w2 * tx, w2 * ty, w2 * tz, w2 * tw);
-                    if (bot && lef) red_add_v4(grad_value + o10, w3 * tx, w3 * ty, w3 * tz, w3 * tw);
-                    if (bot && rig) red_add_v4(grad_value + o11, w4 * tx, w4 * ty, w4 * tz, w4 * tw);
-                }
-                float ga = 0.f, gx = 0.f, gy = 0.f;
-#define MDB_ACC(c)                                                                   \
-    ga = fmaf(g.c, w1 * v1.c + w2 * v2.c + w3 * v3.c + w4 * v4.c, ga);               \
-    gx = fmaf(g.c * a, hy * (v2.c - v1.c) + ly * (v4.c - v3.c), gx);                 \
-    gy = fmaf(g.c * a, hx * (v3.c - v1.c) + lx * (v4.c - v2.c), gy);
-                MDB_ACC(x) MDB_ACC(y) MDB_ACC(z) MDB_ACC(w)
-#undef MDB_ACC
-                const int jx = (l * P + p) * 2, jy = jx + 1, ja = NLOC + l * P + p;
-                vals[(jx % LPU) * PER + jx / LPU] = gx * (float)W;
-                vals[(jy % LPU) * PER + jy / LPU] = gy * (float)H;
-                vals[(ja % LPU) * PER + ja / LPU] = ga;
-            }
-        }
-        {
-            int n = NV;
-#pragma unroll
-            for (int off = LPU / 2; off >= 1; off >>= 1) {
-                n >>= 1;
-                const bool up = (cl & off) != 0;
-#pragma unroll
-                for (int i = 0; i < NV / 2; ++i) {
-                    if (i < n) {
-                        const float send = up ? vals[i] : vals[i + n];
-                        const float keep = up ? vals[i + n] : vals[i];
-                        vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                    }
-                }
-            }
-        }
-        if (live) {
-            float* gl = grad_loc + u * NLOC;
-            float* gat = grad_attn + u * (L * P);
-#pragma unroll
-            for (int i = 0; i < PER; ++i) {
-                const int j = i * LPU + cl;
-                if (i * LPU < NLOC) gl[j] = vals[i];
-                else gat[j - NLOC] = vals[i];
-            }
-        }
-    }
-    __syncthreads();
-    // flush the private rows: one vector reduction per touched (pixel, 4 channels); untouched rows cost nothing
-    float* gv = grad_value + ((size_t)b * S * M + m) * D + (size_t)priv_start * pix;
-    for (int i = threadIdx.x; i < priv_pixels * (D / 4); i += kThreads) {
-        const float4 v = reinterpret_cast<const float4*>(gacc)[i];
-        if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f)
-            red_add_v4(gv + (size_t)(i >> 3) * pix + (i & 7) * 4, v.x, v.y, v.z, v.w);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Generic kernels: one warp per unit, lanes stride over channels; any D, L, P; float and double.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -695,7 +554,7 @@ int forward_impl(const T* value, const int64_t* shapes, const int64_t* lsi, cons
 template <typename T>
 int backward_impl(const T* value, const int64_t* shapes, const int64_t* lsi, const T* loc, const T* attn,
                   const T* grad_out, int B, int S, int M, int D, int L, int Lq, int P, T* grad_value, T* grad_loc,
-                  T* grad_attn, void* stream_, const int64_t* host_shapes = nullptr /* HOST copy of `shapes`, optional */) {
+                  T* grad_attn, void* stream_) {
     int rc = check_common(value, shapes, lsi, loc, attn, B, S, M, D, L, Lq, P);
     if (rc) return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -722,40 +581,11 @@ int backward_impl(const T* value, const int64_t* shapes, const int64_t* lsi, con
             const int grid = grid_for((n_units + upw - 1) / upw, 6);
             const long long per = (kThreads / 32) * upw;
             const long long upb = ((n_units + grid - 1) / grid + per - 1) / per * per;
-            if (lpu == 8) {
-                // Encoder-sized calls: privatise the two coarse levels in shared memory (see msda_bwd_priv_kernel).  The level
-                // sizes must be known on the HOST to size the shared buffer: only callers that pass a host copy of the
-                // shapes (mdb_msda_backward_hs_f32) get this path; levels must be stored back to back in `value`.
-                static const bool no_priv = getenv("MDB_MSDA_NO_PRIV") != nullptr;   // A/B switch (profiling)
-                long long total = 0, priv = 0;
-                if (host_shapes)
-                    for (int l = 0; l < L; ++l) {
-                        const long long hw = host_shapes[2 * l] * host_shapes[2 * l + 1];
-                        total += hw;
-                        if (l >= 2) priv += hw;
-                    }
-                const int priv_pixels = (host_shapes && total == S) ? (int)priv : 0;
-                if (!no_priv && priv_pixels > 0 && priv_pixels < S && priv_pixels * 128 <= 100 * 1024 && Lq >= 2048 && B * M > 0) {
-                    const int smem = priv_pixels * 128;
-                    static bool configured[64] = {};
-                    int dev = 0;
-                    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-                    if (!configured[dev]) {
-                        cudaError_t e = cudaFuncSetAttribute(msda_bwd_priv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-                        if (e != cudaSuccess) return (int)e;
-                        configured[dev] = true;
-                    }
-                    int split = (2 * num_sms() + B * M - 1) / (B * M);
-                    if (split < 1) split = 1;
-                    if (split > (Lq + 255) / 256) split = (Lq + 255) / 256;
-                    const int q_per_part = (((Lq + split - 1) / split) + 3) / 4 * 4;
-                    split = (Lq + q_per_part - 1) / q_per_part;
-                    msda_bwd_priv_kernel<<<B * M * split, kThreads, smem, stream>>>(value, shapes, lsi, loc, attn, grad_out, S, M, Lq, split,
-                                                                                  q_per_part, 2, S - priv_pixels, priv_pixels, grad_value, grad_loc, grad_attn);
-                    return (int)cudaGetLastError();
-                }
+            // (A variant that privatised the two coarse levels' gradient rows in shared memory -- shared-memory atomics, one flush
+            // per CTA -- was measured 2.6x SLOWER at B=8, Lq=10200 (2.51 vs 0.95 ms): the 600 coarse pixels serialise far worse
+            // in one SM's shared-memory atomic unit than spread over the L2 slices.  gpurun r2_msda1.log; removed.)
+            if (lpu == 8)
                 msda_bwd_vec_kernel<8, 4><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, grad_out, S, M, Lq, n_units, upb, grad_value, grad_loc, grad_attn);
-            }
             else if (lpu == 4)
                 msda_bwd_vec_kernel<4, 4><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, grad_out, S, M, Lq, n_units, upb, grad_value, grad_loc, grad_attn);
             else
@@ -787,12 +617,6 @@ int mdb_msda_backward_f32(const float* value, const int64_t* spatial_shapes, con
                           int M, int D, int L, int Lq, int P, float* grad_value, float* grad_loc, float* grad_attn,
                           void* stream) {
     return backward_impl<float>(value, spatial_shapes, level_start, sampling_loc, attn_weight, grad_out, B, S, M, D, L, Lq, P, grad_value, grad_loc, grad_attn, stream);
-}
-int mdb_msda_backward_hs_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start,
-                             const int64_t* host_spatial_shapes, const float* sampling_loc, const float* attn_weight,
-                             const float* grad_out, int B, int S, int M, int D, int L, int Lq, int P, float* grad_value,
-                             float* grad_loc, float* grad_attn, void* stream) {
-    return backward_impl<float>(value, spatial_shapes, level_start, sampling_loc, attn_weight, grad_out, B, S, M, D, L, Lq, P, grad_value, grad_loc, grad_attn, stream, host_spatial_shapes);
 }
 int mdb_msda_backward_f64(const double* value, const int64_t* spatial_shapes, const int64_t* level_start,
                           const double* sampling_loc, const double* attn_weight, const double* grad_out, int B, int S,

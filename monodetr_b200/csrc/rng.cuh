@@ -43,9 +43,16 @@ __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t x) {   // MurmurHas
 __host__ __device__ __forceinline__ uint32_t rng_key32(uint64_t seed, uint64_t stream) {
     return (uint32_t)(fmix64(stream * 0x9E3779B97F4A7C15ull + seed) >> 17);
 }
-// true with probability 1 - thr / 2^32
-__host__ __device__ __forceinline__ bool rng_keep32(uint32_t key, uint32_t idx, uint32_t thr) {
-    return fmix32(idx * 0x9E3779B1u + key) >= thr;
+// Keep decisions of the attention-probability dropout: ONE hash serves the two elements 2k and 2k+1 (16 bits each), so a
+// kernel that walks a row in pairs pays half the hashing.  keep(idx) is true with probability 1 - thr16 / 65536,
+// thr16 = rng_thr16(drop_p).  The same pure function in every kernel (forward, both backward kernels, tensor-core forward).
+__host__ __device__ __forceinline__ uint32_t rng_pair32(uint32_t key, uint32_t pair) { return fmix32(pair * 0x9E3779B1u + key); }
+__host__ __device__ __forceinline__ uint32_t rng_thr16(float drop_p) {
+    const float t = drop_p * 65536.f;
+    return t >= 65535.f ? 65535u : (uint32_t)t;
+}
+__host__ __device__ __forceinline__ bool rng_keep16(uint32_t key, uint32_t idx, uint32_t thr16) {
+    return ((rng_pair32(key, idx >> 1) >> ((idx & 1u) * 16u)) & 0xFFFFu) >= thr16;
 }
 
 }  // namespace mdb

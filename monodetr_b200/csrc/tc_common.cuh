@@ -50,7 +50,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a protocol bug becomes a trap (launch failure) after ~2 s instead of a hung GPU.  The timer is read
 // in a NOINLINE slow path once per 16384 failed polls: reading %globaltimer in the poll loop itself (which the compiler
 // happily if-converts into every iteration) adds its latency to EVERY producer/consumer hand-off of the pipeline.
-__device__ __noinline__ void mbar_slow_path(uint64_t& t0) {
+static __device__ __noinline__ void mbar_slow_path(uint64_t& t0) {
     uint64_t t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     if (t0 == 0) t0 = t;

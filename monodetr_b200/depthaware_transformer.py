@@ -240,8 +240,6 @@ class DepthAwareTransformer(nn.Module):
         if key not in cache:
             ss = torch.as_tensor(shapes, dtype=torch.long, device=dev)
             cache[key] = (ss, torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1])))
-            from .msda import register_host_shapes
-            register_host_shapes(ss, shapes)                   # the encoder-sized backward sizes its smem from these
         return cache[key]
 
     def forward(self, srcs, masks, pos_embeds, query_embed=None, depth_pos_embed=None, depth_pos_embed_ip=None, attn_mask=None):

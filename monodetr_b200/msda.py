@@ -15,28 +15,6 @@ from . import _lib
 
 PROBE = None    # set to a list by bench.py to collect (start_event, stop_event, B, Lq) per forward launch
 
-# Host copies of spatial_shapes tensors.  The pybind signature (vision.cpp:15) only carries DEVICE tensors, while the
-# encoder-sized backward wants the level sizes on the host to size its shared-memory accumulators.  Callers that built the
-# tensor from Python numbers register them here (no synchronisation); any other tensor is read back ONCE per
-# (storage, version) -- never during CUDA-graph capture, where the call simply takes the general kernel.
-_HOST_SHAPES = {}
-
-
-def register_host_shapes(spatial_shapes, shapes):
-    _HOST_SHAPES[(spatial_shapes.data_ptr(), spatial_shapes._version)] = tuple(int(v) for hw in shapes for v in hw)
-
-
-def _host_shapes(spatial_shapes):
-    key = (spatial_shapes.data_ptr(), spatial_shapes._version)
-    hs = _HOST_SHAPES.get(key)
-    if hs is None:
-        if torch.cuda.is_current_stream_capturing():
-            return None
-        if len(_HOST_SHAPES) > 64:
-            _HOST_SHAPES.clear()
-        hs = _HOST_SHAPES[key] = tuple(int(v) for v in spatial_shapes.reshape(-1).tolist())
-    return hs
-
 
 def _check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, extra=()):
     tensors = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
@@ -99,19 +77,11 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     grad_value = torch.empty_like(value)          # zero-filled inside the C call
     grad_loc = torch.empty_like(sampling_loc)
     grad_attn = torch.empty_like(attn_weight)
-    hs = _host_shapes(spatial_shapes) if (value.dtype == torch.float32 and Lq >= 2048 and L == 4) else None
+    fn = _lib.lib().mdb_msda_backward_f32 if value.dtype == torch.float32 else _lib.lib().mdb_msda_backward_f64
     with torch.cuda.device(value.device):
-        if hs is not None:
-            import ctypes
-            rc = _lib.lib().mdb_msda_backward_hs_f32(
-                value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), (ctypes.c_int64 * len(hs))(*hs),
-                sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(), B, S, M, D, L, Lq, P,
-                grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(), _stream())
-        else:
-            fn = _lib.lib().mdb_msda_backward_f32 if value.dtype == torch.float32 else _lib.lib().mdb_msda_backward_f64
-            rc = fn(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
-                    attn_weight.data_ptr(), grad_output.data_ptr(), B, S, M, D, L, Lq, P, grad_value.data_ptr(),
-                    grad_loc.data_ptr(), grad_attn.data_ptr(), _stream())
+        rc = fn(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),
+                attn_weight.data_ptr(), grad_output.data_ptr(), B, S, M, D, L, Lq, P, grad_value.data_ptr(),
+                grad_loc.data_ptr(), grad_attn.data_ptr(), _stream())
     _lib.check(rc, "ms_deform_attn_backward")
     _lib.count(1)
     return [grad_value, grad_loc, grad_attn]

@@ -12,7 +12,7 @@ from monodetr_b200.bench_model import surrogate_loss, synthetic_batch  # noqa: E
 from monodetr_b200.monodetr import DEFAULT_MODEL_CFG  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-tc.set_precision(os.environ.get("MDB_PRECISION", "tf32x3"))
+tc.set_precision(os.environ.get("MDB_PRECISION", "bf16x3"))
 torch.manual_seed(0)
 model, _ = build_monodetr(DEFAULT_MODEL_CFG)
 INFER = len(sys.argv) > 2 and sys.argv[2] == "infer"
