@@ -199,6 +199,16 @@ int mdb_maxpool3x3s2_nhwc_f32(const float* x, float* y, int B, int H, int W, int
 int mdb_depth_sample_forward_f32(const float* depth, const float* xy, float* out, int B, int H, int W, int N, void* stream);
 int mdb_depth_sample_backward_f32(const float* dout, const float* xy, float* ddepth, int B, int H, int W, int N, void* stream);
 
+/* ---- Fused AdamW over flat buffers (optim.cu) -- lib/helpers/optimizer_helper.py:69-129 (the reference's AdamW.step) ----
+ * p, g, m, v: n floats each, 16-byte aligned; elements [0, n_decay) get `weight_decay`, the rest 0 (the reference's
+ * 'bias' in name -> no decay rule, optimizer_helper.py:9-16, realised by the flat ordering).  step_size =
+ * lr * sqrt(1 - beta2^t) / (1 - beta1^t) is computed by the caller: as a host float, or -- step_size_dev != NULL -- read from
+ * device memory at run time (a captured CUDA graph then sees the new value every replay).  one_minus_beta* are passed
+ * separately so that they are the fp32 roundings of the DOUBLE expressions 1 - beta*, as in the reference. */
+int mdb_adamw_step_f32(float* p, const float* g, float* m, float* v, long long n, long long n_decay, float beta1,
+                       float one_minus_beta1, float beta2, float one_minus_beta2, float eps, float weight_decay,
+                       float step_size, const float* step_size_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -199,7 +199,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
         const bool drop_on = p.drop_p > 0.f;
         const float inv_keep = 1.f / (1.f - p.drop_p);
-        const uint32_t thr16 = rng_thr16(p.drop_p);
+        const uint32_t thr32 = rng_thr16(p.drop_p) << 16;
         uint32_t key = 0u;
         if (drop_on) key = rng_key32(*p.seed + p.site * 0x9E3779B97F4A7C15ull, (unsigned long long)(b * p.H + h));
         const uint32_t row_base = (uint32_t)qi * (uint32_t)p.Lk;
@@ -293,18 +293,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
                     }
                     lsum0 += p0;
                     lsum1 += p1;
-                    if (drop_on) {
+                    if (drop_on) {      // (the 1 / (1 - p) factor is applied once, to O, in the epilogue)
                         bool k0b, k1b;
                         if (paired) {
                             const uint32_t hsh = rng_pair32(key, (jb >> 1) + (uint32_t)e);
-                            k0b = (hsh & 0xFFFFu) >= thr16;
-                            k1b = (hsh >> 16) >= thr16;
+                            k0b = hsh >= thr32;
+                            k1b = rng_pair32_odd(hsh) >= thr32;
                         } else {
-                            k0b = rng_keep16(key, jb + 2u * e, thr16);
-                            k1b = rng_keep16(key, jb + 2u * e + 1u, thr16);
+                            k0b = rng_keep16(key, jb + 2u * e, thr32 >> 16);
+                            k1b = rng_keep16(key, jb + 2u * e + 1u, thr32 >> 16);
                         }
-                        p0 = k0b ? p0 * inv_keep : 0.f;
-                        p1 = k1b ? p1 * inv_keep : 0.f;
+                        p0 = k0b ? p0 : 0.f;
+                        p1 = k1b ? p1 : 0.f;
                     }
                     const uint32_t hh = pack_bf16x2(p0, p1);
                     hw[e] = hh;
@@ -358,7 +358,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
             const float a0 = (m_ref == -INFINITY) ? 0.f : ex2_approx((m_ref - m) * kLog2e);
             const float a1 = (m1 == -INFINITY) ? 0.f : ex2_approx((m1 - m) * kLog2e);
             const float l = l_run * a0 + l1 * a1;
-            const float inv = l > 0.f ? 1.f / l : 0.f;
+            const float inv = l > 0.f ? (drop_on ? inv_keep : 1.f) / l : 0.f;
             const float s0 = a0 * inv, s1 = a1 * inv;
             float* dst = p.out + ((size_t)b * p.Lq + qi) * p.ldo + h * kHD;
 #pragma unroll

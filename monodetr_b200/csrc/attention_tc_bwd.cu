@@ -165,12 +165,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
     } else if (warp < 4) {
         // converters: 64 threads.  Q (scaled) and dO once, two rows per thread; then K, V (+ K^T) of every stage, one row each
         const int t = (warp - 2) * 32 + lane;                      // 0..63
+        const float gscale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
         mbar_wait(qg_full, 0);
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             const int row = t + rr * 64;
             split_row_in_place(sQ + row * 128, row, p.scale);
-            split_row_in_place(sG + row * 128, row, 1.f);
+            split_row_in_place(sG + row * 128, row, gscale);       // dO / (1 - p): dP arrives with the dropout scale folded in
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -193,8 +194,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
         const int qi = q0 + r;
         const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
         const bool drop_on = p.drop_p > 0.f;
-        const float inv_keep = 1.f / (1.f - p.drop_p);
-        const uint32_t thr16 = rng_thr16(p.drop_p);
+        const uint32_t thr32 = rng_thr16(p.drop_p) << 16;
         uint32_t key = 0u;
         if (drop_on) key = rng_key32(*p.seed + p.site * 0x9E3779B97F4A7C15ull, (unsigned long long)(b * p.H + h));
         const uint32_t row_base = (uint32_t)qi * (uint32_t)p.Lk;
@@ -233,18 +233,18 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
                         if ((dead >> (2 * e + 1)) & 1u) p1 = 0.f;
                     }
                     float d0 = __uint_as_float(dv[2 * e]), d1 = __uint_as_float(dv[2 * e + 1]);
-                    if (drop_on) {
+                    if (drop_on) {      // (dP already carries 1 / (1 - p): dO was scaled when it was split)
                         bool k0b, k1b;
                         if (paired) {
                             const uint32_t hsh = rng_pair32(key, (jb >> 1) + (uint32_t)e);
-                            k0b = (hsh & 0xFFFFu) >= thr16;
-                            k1b = (hsh >> 16) >= thr16;
+                            k0b = hsh >= thr32;
+                            k1b = rng_pair32_odd(hsh) >= thr32;
                         } else {
-                            k0b = rng_keep16(key, jb + 2u * e, thr16);
-                            k1b = rng_keep16(key, jb + 2u * e + 1u, thr16);
+                            k0b = rng_keep16(key, jb + 2u * e, thr32 >> 16);
+                            k1b = rng_keep16(key, jb + 2u * e + 1u, thr32 >> 16);
                         }
-                        d0 = k0b ? d0 * inv_keep : 0.f;
-                        d1 = k1b ? d1 * inv_keep : 0.f;
+                        d0 = k0b ? d0 : 0.f;
+                        d1 = k1b ? d1 : 0.f;
                     }
                     const float s0 = p0 * (d0 - dl), s1 = p1 * (d1 - dl);
                     const uint32_t hh = pack_bf16x2(s0, s1);
@@ -405,6 +405,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
         }
     } else if (warp < 4) {
         const int t = (warp - 2) * 32 + lane;                      // 0..63
+        const float gscale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
         mbar_wait(kv_full, 0);
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
@@ -431,9 +432,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
             stats[t] = (l == INFINITY) ? -INFINITY : -l * kLog2e;   // exp2 offset of query t
             stats[64 + t] = d;
             transpose_row_bf16(st + t * 128, t, st + 2 * kSmallTile, kSmallTile / 2);                // Q^T
-            transpose_row_bf16(st + kSmallTile + t * 128, t, st + 3 * kSmallTile, kSmallTile / 2);   // dO^T
+            transpose_row_bf16(st + kSmallTile + t * 128, t, st + 3 * kSmallTile, kSmallTile / 2);   // dO^T (unscaled: dV is scaled at the end)
             split_row_in_place(st + t * 128, t, 1.f);
-            split_row_in_place(st + kSmallTile + t * 128, t, 1.f);
+            split_row_in_place(st + kSmallTile + t * 128, t, gscale);   // dO / (1 - p) -> dP^T carries the dropout scale
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&qg_ready[s]);
@@ -445,10 +446,13 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
         const int kj = kbase + r;
         const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
         const bool drop_on = p.drop_p > 0.f;
-        const float inv_keep = 1.f / (1.f - p.drop_p);
+        const float inv_keep = drop_on ? 1.f / (1.f - p.drop_p) : 1.f;
         const uint32_t thr16 = rng_thr16(p.drop_p);
         uint32_t key = 0u;
         if (drop_on) key = rng_key32(*p.seed + p.site * 0x9E3779B97F4A7C15ull, (unsigned long long)(b * p.H + h));
+        // keep(query i, key kj) is element i * Lk + kj of the mask: with Lk even, lanes 2m and 2m+1 (keys kj, kj + 1) share the
+        // pair word, so every lane hashes only the query columns of its own parity and fetches the others from its neighbour
+        const bool share = drop_on && ((p.Lk & 1) == 0) && ((kbase & 1) == 0);
         const bool dead = kj >= p.Lk || (p.kpm && p.kpm[(size_t)b * p.Lk + min(kj, p.Lk - 1)]);
         for (int j = 0; j < n_q; ++j) {
             const int s = j % kKvStages;
@@ -475,12 +479,22 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
                         float p1 = dead ? 0.f : ex2_approx(fmaf(__uint_as_float(sv[2 * ee + 1]), kLog2e, mn.y));
                         float d0 = __uint_as_float(dv[2 * ee]), d1 = __uint_as_float(dv[2 * ee + 1]);
                         float w0 = p0, w1 = p1;
-                        if (drop_on) {
+                        if (drop_on) {      // (1 / (1 - p): dP^T carries it already, dV gets it in the epilogue)
                             const uint32_t qa = (uint32_t)(j * kCols + i0);
-                            const bool k0b = rng_keep16(key, qa * (uint32_t)p.Lk + (uint32_t)kj, thr16);
-                            const bool k1b = rng_keep16(key, (qa + 1u) * (uint32_t)p.Lk + (uint32_t)kj, thr16);
-                            w0 = k0b ? w0 * inv_keep : 0.f; d0 = k0b ? d0 * inv_keep : 0.f;
-                            w1 = k1b ? w1 * inv_keep : 0.f; d1 = k1b ? d1 * inv_keep : 0.f;
+                            bool k0b, k1b;
+                            if (share) {
+                                // this lane hashes column i0 + (lane & 1), the neighbour the other one: word of pair (kj >> 1)
+                                const uint32_t mine = rng_pair32(key, ((qa + (uint32_t)(lane & 1)) * (uint32_t)p.Lk + (uint32_t)kj) >> 1);
+                                const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                                const uint32_t h0 = (lane & 1) ? other : mine, h1 = (lane & 1) ? mine : other;
+                                k0b = ((lane & 1) ? rng_pair32_odd(h0) : h0) >= (thr16 << 16);
+                                k1b = ((lane & 1) ? rng_pair32_odd(h1) : h1) >= (thr16 << 16);
+                            } else {
+                                k0b = rng_keep16(key, qa * (uint32_t)p.Lk + (uint32_t)kj, thr16);
+                                k1b = rng_keep16(key, (qa + 1u) * (uint32_t)p.Lk + (uint32_t)kj, thr16);
+                            }
+                            w0 = k0b ? w0 : 0.f; d0 = k0b ? d0 : 0.f;
+                            w1 = k1b ? w1 : 0.f; d1 = k1b ? d1 : 0.f;
                         }
                         const float s0 = p0 * (d0 - dl.x), s1 = p1 * (d1 - dl.y);
                         const uint32_t ph = pack_bf16x2(w0, w1);
@@ -517,8 +531,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_co
             for (int e = 0; e < 8; ++e) {
                 *reinterpret_cast<float4*>(dkp + 4 * e) = make_float4(__uint_as_float(ok[4 * e]) * p.scale, __uint_as_float(ok[4 * e + 1]) * p.scale,
                                                                       __uint_as_float(ok[4 * e + 2]) * p.scale, __uint_as_float(ok[4 * e + 3]) * p.scale);
-                *reinterpret_cast<float4*>(dvp + 4 * e) = make_float4(__uint_as_float(ov[4 * e]), __uint_as_float(ov[4 * e + 1]),
-                                                                      __uint_as_float(ov[4 * e + 2]), __uint_as_float(ov[4 * e + 3]));
+                *reinterpret_cast<float4*>(dvp + 4 * e) = make_float4(__uint_as_float(ov[4 * e]) * inv_keep, __uint_as_float(ov[4 * e + 1]) * inv_keep,
+                                                                      __uint_as_float(ov[4 * e + 2]) * inv_keep, __uint_as_float(ov[4 * e + 3]) * inv_keep);
             }
         }
         tc_fence_before();

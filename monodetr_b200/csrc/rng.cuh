@@ -43,16 +43,27 @@ __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t x) {   // MurmurHas
 __host__ __device__ __forceinline__ uint32_t rng_key32(uint64_t seed, uint64_t stream) {
     return (uint32_t)(fmix64(stream * 0x9E3779B97F4A7C15ull + seed) >> 17);
 }
-// Keep decisions of the attention-probability dropout: ONE hash serves the two elements 2k and 2k+1 (16 bits each), so a
-// kernel that walks a row in pairs pays half the hashing.  keep(idx) is true with probability 1 - thr16 / 65536,
-// thr16 = rng_thr16(drop_p).  The same pure function in every kernel (forward, both backward kernels, tensor-core forward).
-__host__ __device__ __forceinline__ uint32_t rng_pair32(uint32_t key, uint32_t pair) { return fmix32(pair * 0x9E3779B1u + key); }
+// Keep decisions of the attention-probability dropout: ONE hash serves the two elements 2k and 2k+1, and a decision is a
+// single unsigned compare of the hash against thr16 << 16 (i.e. of its top 16 bits against thr16), so a kernel that walks a
+// row in pairs pays ~3.5 integer instructions per element (the elementwise phase of the tensor-core attention kernels is
+// instruction-bound, and the previous fmix32-per-element mask doubled it).  keep(idx) is true with probability
+// 1 - thr16 / 65536, thr16 = rng_thr16(drop_p).  The same pure function in every kernel (both forwards, all backwards).
+__host__ __device__ __forceinline__ uint32_t rng_pair32(uint32_t key, uint32_t pair) {   // decision word of element 2 * pair
+    uint32_t x = pair * 0x9E3779B1u + key;
+    x ^= x >> 15;
+    x *= 0x2C1B3C6Du;
+    x ^= x >> 12;
+    return x;
+}
+__host__ __device__ __forceinline__ uint32_t rng_pair32_odd(uint32_t h) { return h * 0x297A2D39u; }   // ... of element 2 * pair + 1
 __host__ __device__ __forceinline__ uint32_t rng_thr16(float drop_p) {
     const float t = drop_p * 65536.f;
     return t >= 65535.f ? 65535u : (uint32_t)t;
 }
 __host__ __device__ __forceinline__ bool rng_keep16(uint32_t key, uint32_t idx, uint32_t thr16) {
-    return ((rng_pair32(key, idx >> 1) >> ((idx & 1u) * 16u)) & 0xFFFFu) >= thr16;
+    uint32_t h = rng_pair32(key, idx >> 1);
+    if (idx & 1u) h = rng_pair32_odd(h);
+    return h >= (thr16 << 16);
 }
 
 }  // namespace mdb

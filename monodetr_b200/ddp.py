@@ -23,7 +23,14 @@ class FlatGradBucket:
     tensors are remembered separately, so re-pointing `.grad` never changes what the next replay's pack reads."""
 
     def __init__(self, model, views=False):
-        self.params = [p for n, p in model.named_parameters() if p.requires_grad and not any(s in n for s in _NEVER_USED)]
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and not any(s in n for s in _NEVER_USED)]
+        # Bucket order = weight-decay tensors first, then the tensors with 'bias' in their name (the reference's optimizer
+        # grouping, lib/helpers/optimizer_helper.py:9-16): the fused AdamW (monodetr_b200.optim) then needs one boundary
+        # index (`n_decay`, in elements) instead of a per-tensor table.
+        named = [(n, p) for n, p in named if "bias" not in n] + [(n, p) for n, p in named if "bias" in n]
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        self.n_decay = sum(p.numel() for n, p in named if "bias" not in n)
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)

@@ -14,7 +14,7 @@ H, W = (int(sys.argv[5]), int(sys.argv[6])) if len(sys.argv) > 6 else (96, 320)
 B = 8
 x = torch.randn(B, H, W, Cin, device="cuda")
 w = torch.randn(Cout, Cin, k, k, device="cuda") / (Cin * k * k) ** 0.5
-wp = tc.pack_weight(w)
+wp = tc.split_weights([w])[0] if tc.get_precision() == "bf16x3" else tc.pack_weight(w)
 y = tc.conv2d_forward(x, wp, None, None, k, k, 1, k // 2)
 dy, res = torch.randn_like(y), torch.randn_like(y)
 for _ in range(5):
