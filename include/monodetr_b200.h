@@ -199,6 +199,36 @@ int mdb_maxpool3x3s2_nhwc_f32(const float* x, float* y, int B, int H, int W, int
 int mdb_depth_sample_forward_f32(const float* depth, const float* xy, float* out, int B, int H, int W, int N, void* stream);
 int mdb_depth_sample_backward_f32(const float* dout, const float* xy, float* ddepth, int B, int H, int W, int N, void* stream);
 
+/* ---- Fused elementwise chains around the heads and the depth predictor's tail (heads.cu) -----------------------------------
+ * box refinement (depthaware_transformer.py:602-613): y[n][6] = sigmoid(tmp + inverse_sigmoid(ref)) on the first ref_dim (2 or 6)
+ * components, inverse_sigmoid as utils/misc.py:473-477; backward: dtmp, and dref when non-NULL. */
+int mdb_box_refine_forward_f32(const float* tmp, const float* ref, float* y, long long n, int ref_dim, void* stream);
+int mdb_box_refine_backward_f32(const float* dy, const float* y, const float* ref, float* dtmp, float* dref /*or NULL*/, long long n,
+                                int ref_dim, void* stream);
+/* depth of a query (monodetr.py:230-262): out[b][q] = ((1/(sigmoid(reg0)+1e-6) - 1) + size3d0 / clamp((c4+c5)*img_h, 1) * fu +
+ * grid_sample(weighted_depth, (c01 - 0.5)*2, bilinear, zeros, align_corners=True)) / 3 , reg1.  coord (B,N,6), size3d (B,N,3),
+ * depth_reg (B,N,2), wdepth (B,H,W), calibs (B,3,4), img_sizes (B,2) = [W, H].  backward: dwdepth is zero-filled by the call. */
+int mdb_head_depth_forward_f32(const float* coord, const float* size3d, const float* depth_reg, const float* wdepth, const float* calibs,
+                               const float* img_sizes, float* out, int B, int N, int H, int W, void* stream);
+int mdb_head_depth_backward_f32(const float* dout, const float* coord, const float* size3d, const float* depth_reg, const float* calibs,
+                                const float* img_sizes, float* dcoord, float* dsize3d, float* dreg, float* dwdepth, int B, int N, int H,
+                                int W, void* stream);
+/* depth predictor tail (depth_predictor.py:74-104): per pixel softmax over nb (<= 96) bin logits, weighted depth = sum p * bins,
+ * ip = lerp of the embedding rows floor / floor+1 of clamp(depth, 0, dmax).  logits (npix, nb), emb (E, C), C % 4 == 0, C <= 256.
+ * backward: d_wd_ext (npix) = gradient reaching weighted_depth from elsewhere, or NULL; demb is zero-filled by the call. */
+int mdb_depth_tail_forward_f32(const float* logits, const float* bins, const float* emb, float* wdepth, float* ip, long long npix, int nb,
+                               int E, int C, float dmax, void* stream);
+int mdb_depth_tail_backward_f32(const float* logits, const float* bins, const float* emb, const float* d_ip, const float* d_wd_ext,
+                                float* dlogits, float* demb, long long npix, int nb, int E, int C, float dmax, void* stream);
+/* (a + b + c) / 3 and a * s; n % 4 == 0 */
+int mdb_mean3_f32(const float* a, const float* b, const float* c, float* out, long long n, void* stream);
+int mdb_scale_f32(const float* a, float* out, long long n, float s, void* stream);
+/* loss = sum_k mean(x_k^2) over `count` (<= 32) tensors (the surrogate loss of bench.py's step) and its gradient
+ * g_k = 2 x_k / n_k * dloss; x / g / n are HOST arrays, loss / dloss device scalars. */
+int mdb_sum_mean_squares_forward_f32(int count, const float* const* x, const long long* n, float* loss, void* stream);
+int mdb_sum_mean_squares_backward_f32(int count, const float* const* x, float* const* g, const long long* n, const float* dloss,
+                                      void* stream);
+
 /* ---- Fused AdamW over flat buffers (optim.cu) -- lib/helpers/optimizer_helper.py:69-129 (the reference's AdamW.step) ----
  * p, g, m, v: n floats each, 16-byte aligned; elements [0, n_decay) get `weight_decay`, the rest 0 (the reference's
  * 'bias' in name -> no decay rule, optimizer_helper.py:9-16, realised by the flat ordering).  step_size =

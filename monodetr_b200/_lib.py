@@ -51,6 +51,16 @@ SIGNATURES = {
     "mdb_maxpool3x3s2_nhwc_f32": [_PTR] * 2 + [c_int] * 4 + [_PTR],
     "mdb_depth_sample_forward_f32": [_PTR] * 3 + [c_int] * 4 + [_PTR],
     "mdb_depth_sample_backward_f32": [_PTR] * 3 + [c_int] * 4 + [_PTR],
+    "mdb_box_refine_forward_f32": [_PTR] * 3 + [ctypes.c_longlong, c_int, _PTR],
+    "mdb_box_refine_backward_f32": [_PTR] * 5 + [ctypes.c_longlong, c_int, _PTR],
+    "mdb_head_depth_forward_f32": [_PTR] * 7 + [c_int] * 4 + [_PTR],
+    "mdb_head_depth_backward_f32": [_PTR] * 10 + [c_int] * 4 + [_PTR],
+    "mdb_depth_tail_forward_f32": [_PTR] * 5 + [ctypes.c_longlong, c_int, c_int, c_int, c_float, _PTR],
+    "mdb_depth_tail_backward_f32": [_PTR] * 7 + [ctypes.c_longlong, c_int, c_int, c_int, c_float, _PTR],
+    "mdb_mean3_f32": [_PTR] * 4 + [ctypes.c_longlong, _PTR],
+    "mdb_scale_f32": [_PTR] * 2 + [ctypes.c_longlong, c_float, _PTR],
+    "mdb_sum_mean_squares_forward_f32": [c_int, _PTR, _PTR, _PTR, _PTR],
+    "mdb_sum_mean_squares_backward_f32": [c_int, _PTR, _PTR, _PTR, _PTR, _PTR],
     "mdb_adamw_step_f32": [_PTR] * 4 + [ctypes.c_longlong] * 2 + [c_float] * 7 + [_PTR, _PTR],
 }
 _RESTYPES = {"mdb_error_string": ctypes.c_char_p, "mdb_conv2d_forward_workspace_bytes": ctypes.c_longlong}

@@ -22,15 +22,16 @@ FULL_S = 10200
 
 
 def surrogate_loss(out):
-    loss = 0.0
+    """sum_k mean(out_k^2) over every head output incl. the aux levels, as one fused launch."""
+    from . import functional as Fn
+    ts = []
     for k, v in out.items():
         if k == "aux_outputs":
             for aux in v:
-                for t in aux.values():
-                    loss = loss + (t ** 2).mean()
+                ts.extend(aux.values())
         else:
-            loss = loss + (v ** 2).mean()
-    return loss
+            ts.append(v)
+    return Fn.sum_mean_squares(ts)
 
 
 def synthetic_batch(B, seed):

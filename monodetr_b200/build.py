@@ -19,7 +19,7 @@ SO = os.path.join(HERE, "libmonodetr_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-          "-Xptxas", "-v"]
+          "-Xptxas", "-v"] + (["-DMDB_TIMELINE"] if os.environ.get("MDB_TIMELINE") else [])   # profiling build: tools/diag_timeline.py
 
 
 def _newer(target, deps):

@@ -28,6 +28,16 @@
 #include "tc_common.cuh"
 #include "tma_host.cuh"
 
+// Role-timeline instrumentation (tools/diag_timeline.py): compiled in only with -DMDB_TIMELINE (MDB_TIMELINE=1 python -m
+// monodetr_b200.build); the product library carries neither the clock64 stamps nor their predicates.
+#ifdef MDB_TIMELINE
+#define MDB_STAMP(cond, slot) do { if (cond) p.dbg[slot] = clock64(); } while (0)
+#define MDB_DBG(expr) (expr)
+#else
+#define MDB_STAMP(cond, slot) do { } while (0)
+#define MDB_DBG(expr) false
+#endif
+
 namespace {
 
 using namespace mdb;
@@ -215,7 +225,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     const int s = git % STAGES;
                     const uint32_t ph = (git / STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
-                    if (p.dbg && blockIdx.x == 0 && git < 48) p.dbg[384 + git] = clock64();
+                    MDB_STAMP(p.dbg && blockIdx.x == 0 && git < 48, 384 + git);
                     uint8_t* a_dst = smem + s * kStageBytes;
                     uint8_t* b_dst = a_dst + kTileABytes;
                     mbar_arrive_expect_tx(&full_bar[s], kRawBytes);
@@ -266,11 +276,11 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 const Tile t = decode(tix);
                 if (t.iters == 0) continue;
                 const int slot = lt & 1;
-                const bool dbg = p.dbg && blockIdx.x == 0 && lt < 12;
-                if (dbg) p.dbg[256 + lt * 4 + 0] = clock64();
+                [[maybe_unused]] const bool dbg = MDB_DBG(p.dbg && blockIdx.x == 0 && lt < 12);
+                MDB_STAMP(dbg, 256 + lt * 4 + 0);
                 mbar_wait(&tmem_empty[slot], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
                 tc_fence_after();
-                if (dbg) p.dbg[256 + lt * 4 + 1] = clock64();
+                MDB_STAMP(dbg, 256 + lt * 4 + 1);
                 const uint32_t tacc = tmem_base + slot * BN;
                 for (int it = 0; it < t.iters; ++it, ++git) {
                     const int s = git % STAGES;
@@ -322,7 +332,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     umma_commit(&empty_bar[s]);                   // frees the smem stage when these MMAs retire
                 }
                 umma_commit(&tmem_full[slot]);                    // accumulator complete
-                if (dbg) p.dbg[256 + lt * 4 + 2] = clock64();
+                MDB_STAMP(dbg, 256 + lt * 4 + 2);
                 ++lt;
             }
         }
@@ -524,13 +534,13 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             for (int tix = blockIdx.x; tix < p.total_tiles; tix += gridDim.x) {
                 const Tile t = decode(tix);
                 const int slot = lt & 1;
-                const bool dbg = p.dbg && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0 && lt < 12;
-                if (dbg) p.dbg[lt * 16 + 0] = clock64();
+                [[maybe_unused]] const bool dbg = MDB_DBG(p.dbg && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0 && lt < 12);
+                MDB_STAMP(dbg, lt * 16 + 0);
                 if (t.iters > 0) {
                     mbar_wait(&tmem_full[slot], (lt >> 1) & 1);
                     tc_fence_after();
                 }
-                if (dbg) p.dbg[lt * 16 + 1] = clock64();
+                MDB_STAMP(dbg, lt * 16 + 1);
                 const uint32_t taddr_row = tmem_base + slot * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
                 for (int c0 = chunk0; c0 < BN; c0 += kChunkStep) {
@@ -562,7 +572,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     }
                     mbar_wait(&bars[n % kTsBufs], (n / kTsBufs) & 1);     // residual / mask boxes of this chunk have landed
                     if (t.iters > 0) tmem_ld_wait();
-                    if (dbg && c0 < 128) p.dbg[lt * 16 + 2 + (c0 >> 5) * 3] = clock64();
+                    MDB_STAMP(dbg && c0 < 128, lt * 16 + 2 + (c0 >> 5) * 3);
                     uint8_t* prow = buf + lane * 128;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -581,12 +591,12 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     }
                     fence_proxy_async_smem();      // generic-proxy accesses before the TMA unit's reads (store) and later writes (loads)
                     __syncwarp();
-                    if (dbg && c0 < 128) p.dbg[lt * 16 + 3 + (c0 >> 5) * 3] = clock64();
+                    MDB_STAMP(dbg && c0 < 128, lt * 16 + 3 + (c0 >> 5) * 3);
                     if (lane == 0) {
                         tma_store_4d(&mapO, buf, t.n0 + c0, t.x0 + lx0, t.y0 + ly0, t.img + ib0);
                         tma_store_commit();
                     }
-                    if (dbg && c0 < 128) p.dbg[lt * 16 + 4 + (c0 >> 5) * 3] = clock64();
+                    MDB_STAMP(dbg && c0 < 128, lt * 16 + 4 + (c0 >> 5) * 3);
                     ++n;
                 }
                 if (t.iters > 0) {
@@ -608,13 +618,13 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             for (int tix = blockIdx.x; tix < p.total_tiles; tix += gridDim.x) {
                 const Tile t = decode(tix);
                 const int slot = lt & 1;
-                const bool dbg = p.dbg && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0 && lt < 12;
-                if (dbg) p.dbg[lt * 16 + 0] = clock64();
+                [[maybe_unused]] const bool dbg = MDB_DBG(p.dbg && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0 && lt < 12);
+                MDB_STAMP(dbg, lt * 16 + 0);
                 if (t.iters > 0) {
                     mbar_wait(&tmem_full[slot], (lt >> 1) & 1);
                     tc_fence_after();
                 }
-                if (dbg) p.dbg[lt * 16 + 1] = clock64();
+                MDB_STAMP(dbg, lt * 16 + 1);
                 const uint32_t taddr_row = tmem_base + slot * BN + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
                 for (int c0 = chunk0; c0 < BN; c0 += 32 * (EPI / 4)) {
@@ -639,7 +649,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     if (t.iters > 0) tmem_ld_wait();
-                    if (dbg && c0 < 128) p.dbg[lt * 16 + 2 + (c0 >> 5) * 3] = clock64();
+                    MDB_STAMP(dbg && c0 < 128, lt * 16 + 2 + (c0 >> 5) * 3);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
@@ -650,12 +660,12 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     }
                     fence_proxy_async_smem();      // generic-proxy writes -> visible to the TMA unit's async-proxy reads
                     __syncwarp();
-                    if (dbg && c0 < 128) p.dbg[lt * 16 + 3 + (c0 >> 5) * 3] = clock64();
+                    MDB_STAMP(dbg && c0 < 128, lt * 16 + 3 + (c0 >> 5) * 3);
                     if (lane == 0) {
                         tma_store_4d(&mapO, patch, t.n0 + c0, t.x0 + lx0, t.y0 + ly0, t.img + ib0);
                         tma_store_commit();
                     }
-                    if (dbg && c0 < 128) p.dbg[lt * 16 + 4 + (c0 >> 5) * 3] = clock64();
+                    MDB_STAMP(dbg && c0 < 128, lt * 16 + 4 + (c0 >> 5) * 3);
                 }
                 if (t.iters > 0) {
                     tc_fence_before();             // TMEM reads of this warp are done: hand the accumulator back
@@ -695,13 +705,13 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 }
             }
             const int slot = lt & 1;
-            const bool dbg = p.dbg && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0 && lt < 12;
-            if (dbg) p.dbg[lt * 16 + 0] = clock64();
+            [[maybe_unused]] const bool dbg = MDB_DBG(p.dbg && blockIdx.x == 0 && warp == kEpiWarp0 && lane == 0 && lt < 12);
+            MDB_STAMP(dbg, lt * 16 + 0);
             if (t.iters > 0) {
                 mbar_wait(&tmem_full[slot], (lt >> 1) & 1);
                 tc_fence_after();
             }
-            if (dbg) p.dbg[lt * 16 + 1] = clock64();
+            MDB_STAMP(dbg, lt * 16 + 1);
             const uint32_t taddr_row = tmem_base + slot * BN + ((uint32_t)(q * 32) << 16);
             // patch element (row, 16-byte group g) lives at row * 32 + ((g ^ (row & 7)) << 2): conflict-free for the row-per-lane
             // writes (8 lanes = 8 groups) and for the 8-lanes-per-row reads.  This lane reads rows i * 4 + r4, group c4.
@@ -737,12 +747,12 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
                     for (int j = 0; j < 32; ++j) r[j] = 0u;
                 }
-                if (dbg && c0 < 128) p.dbg[lt * 16 + 2 + (c0 >> 5) * 3] = clock64();
+                MDB_STAMP(dbg && c0 < 128, lt * 16 + 2 + (c0 >> 5) * 3);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<uint4*>(patch + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
                 __syncwarp();
-                if (dbg && c0 < 128) p.dbg[lt * 16 + 3 + (c0 >> 5) * 3] = clock64();
+                MDB_STAMP(dbg && c0 < 128, lt * 16 + 3 + (c0 >> 5) * 3);
                 if (full) {
                     // Straight-line, flag-specialised row loop.  With runtime flags inside it the compiler emitted ~66
                     // dependent instructions per row and, with one epilogue warp per scheduler, each 16 KB chunk took
@@ -808,7 +818,7 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     }
                 }
                 __syncwarp();                  // the patch is rewritten by the next chunk
-                if (dbg && c0 < 128) p.dbg[lt * 16 + 4 + (c0 >> 5) * 3] = clock64();
+                MDB_STAMP(dbg && c0 < 128, lt * 16 + 4 + (c0 >> 5) * 3);
             }
             if (t.iters > 0) {
                 tc_fence_before();             // TMEM reads of this warp are done: hand the accumulator back
@@ -1011,7 +1021,9 @@ int check_geom(const ConvGeom& g, bool forward = false) {
 
 extern "C" {
 
+#ifdef MDB_TIMELINE
 void mdb_debug_set_timeline(long long* device_buf) { g_dbg = device_buf; }
+#endif
 
 int mdb_set_precision(int mode) {
     if (mode < 0 || mode > 2) return MDB_EINVAL;

@@ -23,7 +23,7 @@ namespace {
 __device__ __forceinline__ void adamw1(float& p, float g, float& m, float& v, float b1, float omb1, float b2, float omb2, float eps,
                                        float wd, float neg_step) {
     m = fmaf(omb1, g, __fmul_rn(m, b1));
-    v = fmaf(__fmul_rn(omb2, g), g, __fmul_rn(v, b2));
+    v = fmaf(omb2, __fmul_rn(g, g), __fmul_rn(v, b2));        // addcmul_: self + value * (t1 * t2)
     const float denom = __fadd_rn(sqrtf(v), eps);
     const float upd = __fadd_rn(__fmul_rn(p, wd), __fdiv_rn(m, denom));
     p = fmaf(neg_step, upd, p);

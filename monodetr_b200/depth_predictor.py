@@ -99,16 +99,16 @@ class DepthPredictor(nn.Module):
         up = F.interpolate(feature[2].permute(0, 3, 1, 2), size=src_16.shape[1:3], mode="bilinear").permute(0, 2, 3, 1)
         src_32 = self.upsample(up.contiguous())
         src_8 = self.downsample(feature[0])
-        src = (src_8 + src_16 + src_32) / 3
+        src = Fn.mean3(src_8, src_16, src_32)
         h = self.depth_head
         src = Fn.groupnorm_nhwc(Fn.conv2d_nhwc(src, h[0].weight, h[0].bias, 1, 1), h[1].weight, h[1].bias, 32, h[1].eps, True)
         src = Fn.groupnorm_nhwc(Fn.conv2d_nhwc(src, h[3].weight, h[3].bias, 1, 1), h[4].weight, h[4].bias, 32, h[4].eps, True)
         depth_logits = Fn.conv2d_nhwc(src, self.depth_classifier.weight, self.depth_classifier.bias, 1, 0)
-        depth_probs = F.softmax(depth_logits, dim=-1)
-        weighted_depth = (depth_probs * self.depth_bin_values.reshape(1, 1, 1, -1)).sum(dim=-1)
+        # softmax over the bins -> expected depth -> lerp into the depth positional embedding (:74-77, :93-104), one kernel
+        weighted_depth, depth_pos_embed_ip = Fn.depth_tail(depth_logits, self.depth_bin_values, self.depth_pos_embed.weight, self.depth_max)
         B, H, W, C = src.shape
         depth_embed = self.depth_encoder(src.view(B, H * W, C), mask, pos)
-        depth_pos_embed_ip = self.interpolate_depth_embed(weighted_depth).view(B, H * W, C)
+        depth_pos_embed_ip = depth_pos_embed_ip.view(B, H * W, C)
         return depth_logits, depth_embed + depth_pos_embed_ip, weighted_depth, depth_pos_embed_ip
 
     def interpolate_depth_embed(self, depth):

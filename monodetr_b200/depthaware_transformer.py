@@ -190,10 +190,8 @@ class DepthAwareDecoder(nn.Module):
             output = layer(output, query_pos, reference_points_input, src, src_spatial_shapes, src_level_start_index,
                            src_padding_mask, depth_pos_embed, mask_depth, bs)
             tmp = self.bbox_embed[lid](output)                                   # :602-613
-            if reference_points.shape[-1] == 6:
-                new_reference_points = (tmp + inverse_sigmoid(reference_points)).sigmoid()
-            else:
-                new_reference_points = torch.cat((tmp[..., :2] + inverse_sigmoid(reference_points), tmp[..., 2:]), -1).sigmoid()
+            # (tmp + inverse_sigmoid(ref)).sigmoid() on the first 2 / all 6 components: one fused kernel
+            new_reference_points = Fn.box_refine(tmp, reference_points)
             intermediate_boxes.append(new_reference_points)                     # with gradient: == outputs_coord of monodetr.py:216-228
             reference_points = new_reference_points.detach()
             reference_dims = self.dim_embed[lid](output)

@@ -376,3 +376,172 @@ class _DepthSample(Function):
 
 def depth_sample(depth, xy):
     return _DepthSample.apply(depth, xy)
+
+
+# ---- fused elementwise chains around the heads / depth predictor tail (csrc/heads.cu) ----------------------------------
+import ctypes as _ct
+
+
+class _BoxRefine(Function):
+    """sigmoid(tmp + inverse_sigmoid(ref)) on the first ref_dim components (depthaware_transformer.py:602-613)."""
+
+    @staticmethod
+    def forward(ctx, tmp, ref):
+        tmp = tmp.contiguous()
+        refc = ref.detach().contiguous()
+        rd = refc.shape[-1]
+        n = tmp.numel() // 6
+        y = torch.empty_like(tmp)
+        _lib.check(_lib.lib().mdb_box_refine_forward_f32(_p(tmp), _p(refc), _p(y), n, rd, _s()), "box_refine_forward")
+        _lib.count(1)
+        ctx.save_for_backward(y, refc)
+        ctx.meta = (n, rd, ref.shape)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        y, refc = ctx.saved_tensors
+        n, rd, rshape = ctx.meta
+        dy = dy.contiguous()
+        dtmp = torch.empty_like(y)
+        dref = torch.empty(rshape, dtype=torch.float32, device=y.device) if ctx.needs_input_grad[1] else None
+        _lib.check(_lib.lib().mdb_box_refine_backward_f32(_p(dy), _p(y), _p(refc), _p(dtmp), _p(dref), n, rd, _s()), "box_refine_backward")
+        _lib.count(1)
+        return dtmp, dref
+
+
+def box_refine(tmp, ref):
+    return _BoxRefine.apply(tmp, ref)
+
+
+class _HeadDepth(Function):
+    """monodetr.py:230-262: ((1/(sigmoid(reg0)+1e-6) - 1) + geometric depth + depth-map lookup) / 3 and reg1 -> (B, N, 2)."""
+
+    @staticmethod
+    def forward(ctx, coord, size3d, depth_reg, wdepth, calibs, img_sizes):
+        coord, size3d, depth_reg, wdepth = (t.contiguous() for t in (coord, size3d, depth_reg, wdepth))
+        calibs = calibs.contiguous().float()
+        img_sizes = img_sizes.contiguous().float()
+        B, N, _ = coord.shape
+        _, H, W = wdepth.shape
+        out = torch.empty((B, N, 2), dtype=torch.float32, device=coord.device)
+        _lib.check(_lib.lib().mdb_head_depth_forward_f32(_p(coord), _p(size3d), _p(depth_reg), _p(wdepth), _p(calibs), _p(img_sizes), _p(out),
+                                                         B, N, H, W, _s()), "head_depth_forward")
+        _lib.count(1)
+        ctx.save_for_backward(coord, size3d, depth_reg, calibs, img_sizes)
+        ctx.meta = (B, N, H, W)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        coord, size3d, depth_reg, calibs, img_sizes = ctx.saved_tensors
+        B, N, H, W = ctx.meta
+        dout = dout.contiguous()
+        dcoord, dsize, dreg = torch.empty_like(coord), torch.empty_like(size3d), torch.empty_like(depth_reg)
+        dwd = torch.empty((B, H, W), dtype=torch.float32, device=dout.device)
+        _lib.check(_lib.lib().mdb_head_depth_backward_f32(_p(dout), _p(coord), _p(size3d), _p(depth_reg), _p(calibs), _p(img_sizes), _p(dcoord),
+                                                          _p(dsize), _p(dreg), _p(dwd), B, N, H, W, _s()), "head_depth_backward")
+        _lib.count(1)
+        return dcoord, dsize, dreg, dwd, None, None
+
+
+def head_depth(coord, size3d, depth_reg, wdepth, calibs, img_sizes):
+    return _HeadDepth.apply(coord, size3d, depth_reg, wdepth, calibs, img_sizes)
+
+
+class _DepthTail(Function):
+    """depth_predictor.py:74-104: logits (B,H,W,nb) -> weighted_depth (B,H,W), interpolated depth embedding (B,H,W,C)."""
+
+    @staticmethod
+    def forward(ctx, logits, bins, emb, dmax):
+        logits = logits.contiguous()
+        bins = bins.detach().contiguous()
+        embc = emb.contiguous()
+        B, H, W, nb = logits.shape
+        E, C = embc.shape
+        wd = torch.empty((B, H, W), dtype=torch.float32, device=logits.device)
+        ip = torch.empty((B, H, W, C), dtype=torch.float32, device=logits.device)
+        _lib.check(_lib.lib().mdb_depth_tail_forward_f32(_p(logits), _p(bins), _p(embc), _p(wd), _p(ip), B * H * W, nb, E, C, float(dmax), _s()),
+                   "depth_tail_forward")
+        _lib.count(1)
+        ctx.save_for_backward(logits, bins, embc)
+        ctx.meta = (B * H * W, nb, E, C, float(dmax))
+        return wd, ip
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dwd, dip):
+        logits, bins, embc = ctx.saved_tensors
+        npix, nb, E, C, dmax = ctx.meta
+        dip = torch.zeros((npix, C), dtype=torch.float32, device=logits.device) if dip is None else dip.contiguous()
+        dwd = None if dwd is None else dwd.contiguous()
+        dlogits = torch.empty_like(logits)
+        demb = torch.empty_like(embc)
+        _lib.check(_lib.lib().mdb_depth_tail_backward_f32(_p(logits), _p(bins), _p(embc), _p(dip), _p(dwd), _p(dlogits), _p(demb), npix, nb, E, C,
+                                                          dmax, _s()), "depth_tail_backward")
+        _lib.count(1)
+        return dlogits, None, demb, None
+
+
+def depth_tail(logits, bins, emb, dmax):
+    return _DepthTail.apply(logits, bins, emb, dmax)
+
+
+class _Mean3(Function):
+    @staticmethod
+    def forward(ctx, a, b, c):
+        a, b, c = a.contiguous(), b.contiguous(), c.contiguous()
+        out = torch.empty_like(a)
+        _lib.check(_lib.lib().mdb_mean3_f32(_p(a), _p(b), _p(c), _p(out), a.numel(), _s()), "mean3")
+        _lib.count(1)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        g = torch.empty_like(dy)
+        _lib.check(_lib.lib().mdb_scale_f32(_p(dy), _p(g), dy.numel(), 1.0 / 3.0, _s()), "scale")
+        _lib.count(1)
+        return g, g, g
+
+
+def mean3(a, b, c):
+    """(a + b + c) / 3 (depth_predictor.py:66)."""
+    return _Mean3.apply(a, b, c)
+
+
+class _SumMeanSquares(Function):
+    """sum_k mean(x_k^2) over a list of tensors in ONE launch (and one for the backward): the surrogate loss of SURVEY.md 8(d)."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        xs = [x.contiguous() for x in xs]
+        n = len(xs)
+        loss = torch.empty((), dtype=torch.float32, device=xs[0].device)
+        ptrs = (_ct.c_void_p * n)(*[x.data_ptr() for x in xs])
+        nums = (_ct.c_longlong * n)(*[x.numel() for x in xs])
+        _lib.check(_lib.lib().mdb_sum_mean_squares_forward_f32(n, ptrs, nums, _p(loss), _s()), "sum_mean_squares_forward")
+        _lib.count(1)
+        ctx.save_for_backward(*xs)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dloss):
+        xs = ctx.saved_tensors
+        n = len(xs)
+        gs = [torch.empty_like(x) for x in xs]
+        ptrs = (_ct.c_void_p * n)(*[x.data_ptr() for x in xs])
+        gptrs = (_ct.c_void_p * n)(*[g.data_ptr() for g in gs])
+        nums = (_ct.c_longlong * n)(*[x.numel() for x in xs])
+        dl = dloss.contiguous().float()
+        _lib.check(_lib.lib().mdb_sum_mean_squares_backward_f32(n, ptrs, gptrs, nums, _p(dl), _s()), "sum_mean_squares_backward")
+        _lib.count(1)
+        return tuple(gs)
+
+
+def sum_mean_squares(tensors):
+    return _SumMeanSquares.apply(*tensors)

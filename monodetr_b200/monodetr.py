@@ -31,25 +31,6 @@ class _ProjGN(nn.Sequential):
         return Fn.groupnorm_nhwc(y, gn.weight, gn.bias, gn.num_groups, gn.eps, False)
 
 
-def bilinear_sample_align_corners(depth, xy):
-    """F.grid_sample(depth[:, None], xy[:, :, None], bilinear, zeros, align_corners=True) (reference :248-253) written
-    with gathers so it never dispatches to cuDNN's grid sampler.  depth (B, H, W), xy (B, N, 2) in [-1, 1] -> (B, N)."""
-    B, H, W = depth.shape
-    x = (xy[..., 0] + 1) * 0.5 * (W - 1)
-    y = (xy[..., 1] + 1) * 0.5 * (H - 1)
-    x0 = x.floor()
-    y0 = y.floor()
-    lx, ly = x - x0, y - y0
-    flat = depth.reshape(B, H * W)
-
-    def tap(yy, xx):
-        ok = (xx >= 0) & (xx <= W - 1) & (yy >= 0) & (yy <= H - 1)
-        idx = (yy.clamp(0, H - 1) * W + xx.clamp(0, W - 1)).long()
-        return torch.gather(flat, 1, idx) * ok.to(depth.dtype)
-    return (tap(y0, x0) * (1 - ly) * (1 - lx) + tap(y0, x0 + 1) * (1 - ly) * lx
-            + tap(y0 + 1, x0) * ly * (1 - lx) + tap(y0 + 1, x0 + 1) * ly * lx)
-
-
 class MonoDETR(nn.Module):
     """Monocular 3D detector; same constructor as the reference (:30-31)."""
 
@@ -155,14 +136,9 @@ class MonoDETR(nn.Module):
             outputs_classes.append(Fn.linear(hs[lvl], cls.weight, cls.bias))
             size3d = inter_references_dim[lvl]
             outputs_3d_dims.append(size3d)
-            box2d_height_norm = outputs_coord[:, :, 4] + outputs_coord[:, :, 5]
-            box2d_height = torch.clamp(box2d_height_norm * img_sizes[:, 1:2], min=1.0)
-            depth_geo = size3d[:, :, 0] / box2d_height * calibs[:, 0, 0].unsqueeze(1)
             depth_reg = self.depth_embed[lvl](hs[lvl])
-            outputs_center3d = ((outputs_coord[..., :2] - 0.5) * 2).detach()
-            depth_map = Fn.depth_sample(weighted_depth, outputs_center3d).unsqueeze(-1)
-            depth_ave = torch.cat([((1. / (depth_reg[:, :, 0:1].sigmoid() + 1e-6) - 1.) + depth_geo.unsqueeze(-1) + depth_map) / 3,
-                                   depth_reg[:, :, 1:2]], -1)
+            # regressed + geometric + depth-map depth, averaged (:230-262; the sample grid uses detached centres): one kernel
+            depth_ave = Fn.head_depth(outputs_coord, size3d, depth_reg, weighted_depth, calibs, img_sizes)
             outputs_depths.append(depth_ave)
             outputs_angles.append(self.angle_embed[lvl](hs[lvl]))
 

@@ -1,7 +1,7 @@
 """GPU parity of the fused AdamW (csrc/optim.cu, monodetr_b200/optim.py) against the reference's update
 (lib/helpers/optimizer_helper.py:88-127) restated in oracle/optim.py with the same torch operations, run on the SAME device.
 The kernel reproduces torch's per-operation rounding (explicit FMAs where torch's kernels contract, separate roundings
-elsewhere), so the comparison is held to a few ulp: rtol 2e-7 on parameters and both moment buffers."""
+elsewhere), so the comparison is held to a few ulp: rtol 4e-7 on parameters and both moment buffers."""
 import pytest
 import torch
 
@@ -35,13 +35,13 @@ def _check(params, names, opt, steps, lr, wd):
         opt.step()
         adamw_reference_step(ref, grads, ms, vs, step, lr, 0.9, 0.999, 1e-8, wds)
         for p, r, n in zip(params, ref, names):
-            assert torch.allclose(p.detach(), r, rtol=2e-7, atol=1e-9), (n, step, float((p.detach() - r).abs().max()))
+            assert torch.allclose(p.detach(), r, rtol=4e-7, atol=1e-9), (n, step, float((p.detach() - r).abs().max()))
             exact = exact and torch.equal(p.detach(), r)
     off = 0
     for m_ref, v_ref in zip(ms, vs):
         n = m_ref.numel()
-        assert torch.allclose(opt.exp_avg[off:off + n].view_as(m_ref), m_ref, rtol=2e-7, atol=1e-12)
-        assert torch.allclose(opt.exp_avg_sq[off:off + n].view_as(v_ref), v_ref, rtol=2e-7, atol=1e-12)
+        assert torch.allclose(opt.exp_avg[off:off + n].view_as(m_ref), m_ref, rtol=4e-7, atol=1e-12)
+        assert torch.allclose(opt.exp_avg_sq[off:off + n].view_as(v_ref), v_ref, rtol=4e-7, atol=1e-12)
         off += n
     print("bit-exact vs torch's kernels:", exact)
 

@@ -1,4 +1,5 @@
-"""Role timeline (clock64 stamps of CTA 0) of one tcgen05 conv launch: where do the epilogue / MMA / producer wait?"""
+"""Role timeline (clock64 stamps of CTA 0) of one tcgen05 conv launch: where do the epilogue / MMA / producer wait?
+Needs the instrumented build:  MDB_TIMELINE=1 python -m monodetr_b200.build --force   (the product library has no stamps)."""
 import ctypes
 import os
 import sys
