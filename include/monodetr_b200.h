@@ -72,6 +72,16 @@ int mdb_msda_prep_backward_f32(const float* dloc, const float* dattn, const floa
                                const int64_t* spatial_shapes, int B, int Lq, int M, int L, int P, int ref_dim,
                                float* doff, float* dlogits, void* stream);
 
+/* The module's forward with the pre-processing INSIDE the sampling kernels (constant reference points; D = 32, L = 4, P = 4,
+ * otherwise MDB_EUNSUPPORTED): offsets (B,Lq,M,L,P,2) and logits (B,Lq,M,L*P) are the raw projections, ref (B,Lq,L,ref_dim).
+ * backward: grad_value zero-filled then accumulated; grad_offsets / grad_logits fully written. */
+int mdb_msda_fused_forward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start, const float* offsets,
+                               const float* logits, const float* ref, int B, int S, int M, int D, int L, int Lq, int P, int ref_dim,
+                               float* out, void* stream);
+int mdb_msda_fused_backward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start, const float* offsets,
+                                const float* logits, const float* ref, const float* grad_out, int B, int S, int M, int D, int L, int Lq,
+                                int P, int ref_dim, float* grad_value, float* grad_offsets, float* grad_logits, void* stream);
+
 /* ---- Tensor-core convolution / linear family (tcgen05 + TMEM + TMA, fp32 storage, TF32 math) ----
  * Replaces the cuDNN / cuBLAS calls behind nn.Conv2d / nn.Linear on the reference path
  * (backbone.py:100-102; monodetr.py:83-91; depth_predictor/depth_predictor.py:29-47;

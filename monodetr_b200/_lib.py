@@ -20,6 +20,8 @@ SIGNATURES = {
     "mdb_msda_forward_f64": [_PTR] * 5 + [c_int] * 7 + [_PTR, _PTR],
     "mdb_msda_backward_f32": [_PTR] * 6 + [c_int] * 7 + [_PTR] * 4,
     "mdb_msda_backward_f64": [_PTR] * 6 + [c_int] * 7 + [_PTR] * 4,
+    "mdb_msda_fused_forward_f32": [_PTR] * 6 + [c_int] * 8 + [_PTR, _PTR],
+    "mdb_msda_fused_backward_f32": [_PTR] * 7 + [c_int] * 8 + [_PTR] * 4,
     "mdb_msda_prep_forward_f32": [_PTR] * 4 + [c_int] * 6 + [_PTR] * 3,
     "mdb_msda_prep_backward_f32": [_PTR] * 5 + [c_int] * 6 + [_PTR] * 3,
     "mdb_set_precision": [c_int],

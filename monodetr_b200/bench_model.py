@@ -300,7 +300,7 @@ def run(args, rank, local_rank, ws, infer=False, batch_override=None, extras=Tru
                                  "shapes": gemm}
     if enc_ms:
         ach = fwd_bytes / (enc_ms * 1e-3) / 1e9
-        line["roofline"] = {"kernel": "msda_fwd_d32_kernel (encoder call, Lq=10200, in situ)", "bound": "hbm", "achieved": ach,
+        line["roofline"] = {"kernel": "msda_fwd_d32_kernel<fused pre-processing> (encoder call, Lq=10200, in situ)", "bound": "hbm", "achieved": ach,
                             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                             # dram__bytes_read.sum + dram__bytes_write.sum of this launch at B=8 from the committed capture
                             # profiles/r01_msda_fwd_d32_model.txt (239.9 MB + 72.1 MB); scaled with the batch

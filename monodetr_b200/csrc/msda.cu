@@ -175,11 +175,16 @@ __device__ __forceinline__ PointSetup setup_point(float lx_, float ly_, float a,
     return s;
 }
 
+// FUSED: `loc` / `attn` are the RAW projections of the module (sampling offsets (.., L, P, 2) and attention logits (.., L*P)) and
+// the pre-processing of ops/modules/ms_deform_attn.py:145-155 happens here: the softmax over the unit's 16 logits costs two
+// exponentials per lane and six width-8 shuffles, the location arithmetic one divide / FMA per coordinate -- the separate
+// pre-processing kernel and its 125 MB round trip through HBM (encoder call, B = 8) disappear.
+template <bool FUSED>
 __global__ void __launch_bounds__(kThreads, 4)
 msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
-                    const float* __restrict__ attn, int S, int M, int Lq, long long n_units,
-                    long long units_per_block, float* __restrict__ out) {
+                    const float* __restrict__ attn, const float* __restrict__ ref, int ref_dim, int S, int M, int Lq,
+                    long long n_units, long long units_per_block, float* __restrict__ out) {
     constexpr int L = 4, P = 4, D = 32, UPW = 4;
     __shared__ LevelInfo lv;
     if (threadIdx.x < L) {
@@ -206,11 +211,40 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
         const int b = (int)(u / ((long long)Lq * M));
         const float* vb = value + ((size_t)b * S * M + m) * D + cl * 4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        [[maybe_unused]] float e0 = 0.f, e1 = 0.f;
+        if constexpr (FUSED) {                 // softmax over the unit's 16 logits: this lane holds logits cl and 8 + cl
+            const float l0 = __ldg(attn + (size_t)u * (L * P) + cl), l1 = __ldg(attn + (size_t)u * (L * P) + 8 + cl);
+            float mx = fmaxf(l0, l1);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4, 8));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2, 8));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1, 8));
+            e0 = expf(l0 - mx); e1 = expf(l1 - mx);
+            float sum = e0 + e1;
+            sum += __shfl_xor_sync(0xffffffffu, sum, 4, 8);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2, 8);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1, 8);
+            const float inv = 1.f / sum;
+            e0 *= inv; e1 *= inv;
+        }
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             // this lane's point of this half: (l = 2*half + cl/4, p = cl%4)
-            const float2 xy = __ldg(reinterpret_cast<const float2*>(loc + (size_t)u * (L * P * 2)) + half * 8 + cl);
-            const float a = __ldg(attn + (size_t)u * (L * P) + half * 8 + cl);
+            float2 xy = __ldg(reinterpret_cast<const float2*>(loc + (size_t)u * (L * P * 2)) + half * 8 + cl);
+            float a;
+            if constexpr (FUSED) {
+                a = half ? e1 : e0;
+                const int l = half ? lB : lA;
+                const float* r = ref + ((size_t)(u / M) * L + l) * ref_dim;
+                if (ref_dim == 2) {
+                    xy.x = __ldg(r) + xy.x / (float)(half ? WB : WA);
+                    xy.y = __ldg(r + 1) + xy.y / (float)(half ? HB : HA);
+                } else {
+                    xy.x = fmaf(xy.x, (__ldg(r + 2) + __ldg(r + 3)) * 0.5f / (float)P, __ldg(r));
+                    xy.y = fmaf(xy.y, (__ldg(r + 4) + __ldg(r + 5)) * 0.5f / (float)P, __ldg(r + 1));
+                }
+            } else {
+                a = __ldg(attn + (size_t)u * (L * P) + half * 8 + cl);
+            }
             const PointSetup Sx = half ? setup_point(xy.x, xy.y, a, HB, WB, sB, pix) : setup_point(xy.x, xy.y, a, HA, WA, sA, pix);
 #pragma unroll
             for (int jg = 0; jg < 4; ++jg) {             // 2 points = 8 line loads in flight at a time (register budget: 64)
@@ -249,13 +283,18 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
 // ------------------------------------------------------------------------------------------------
 // Fast backward: LPU lanes per unit, D = 4*LPU, L = 4, P = 4 (3*L*P = 48 per-unit outputs).
 // ------------------------------------------------------------------------------------------------
-template <int LPU, int L>
+// FUSED (LPU == 8 only): `loc` / `attn` are the raw sampling offsets / attention logits, `grad_loc` / `grad_attn` receive the
+// gradients wrt THOSE (the softmax / location pre-processing and its backward, ms_deform_attn.py:145-155, run inside this kernel;
+// the reference points are constants of this path -- the caller takes the unfused path when they need a gradient).
+template <int LPU, int L, bool FUSED = false>
 __global__ void __launch_bounds__(kThreads, 2)
 msda_bwd_vec_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lsi, const float* __restrict__ loc,
                     const float* __restrict__ attn, const float* __restrict__ grad_out, int S, int M,
                     int Lq, long long n_units, long long units_per_block, float* __restrict__ grad_value,
-                    float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
+                    float* __restrict__ grad_loc, float* __restrict__ grad_attn, const float* __restrict__ ref = nullptr,
+                    int ref_dim = 0) {
+    static_assert(!FUSED || (LPU == 8 && L == 4), "fused pre-processing: D = 32, L = 4");
     constexpr int D = 4 * LPU;
     constexpr int UPW = 32 / LPU;
     constexpr int P = 4;
@@ -291,6 +330,38 @@ msda_bwd_vec_kernel(const float* __restrict__ value, const int64_t* __restrict__
         const float* ap = attn + (size_t)u * L * P;
         float4 g = ldg4(grad_out + (size_t)u * D + cl * 4);
         if (!live) g = make_float4(0.f, 0.f, 0.f, 0.f);
+        // FUSED: the pre-processing is DISTRIBUTED over the unit's 8 lanes like in the forward kernel -- lane cl prepares points cl
+        // and 8 + cl (two exponentials, two locations) and the level loop fetches what it needs with width-8 shuffles.  (Every lane
+        // preparing all 16 points cost 16 expf + 32 divides per lane and made this kernel 30 % slower than the two-step path.)
+        [[maybe_unused]] float pa[2] = {0.f, 0.f}, px[2] = {0.f, 0.f}, py[2] = {0.f, 0.f};
+        [[maybe_unused]] float sc[L][2];                           // FUSED: d loc / d offset per level (x, y)
+        if constexpr (FUSED) {
+            const float l0 = __ldg(ap + cl), l1 = __ldg(ap + 8 + cl);
+            float mx = fmaxf(l0, l1);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4, 8));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2, 8));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1, 8));
+            pa[0] = expf(l0 - mx); pa[1] = expf(l1 - mx);
+            float sum = pa[0] + pa[1];
+            sum += __shfl_xor_sync(0xffffffffu, sum, 4, 8);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2, 8);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1, 8);
+            const float inv = 1.f / sum;
+            pa[0] *= inv; pa[1] *= inv;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {                       // point hf * 8 + cl = (level 2 hf + cl / 4, point cl % 4)
+                const int l = 2 * hf + (cl >> 2);
+                const float2 o = __ldg(reinterpret_cast<const float2*>(lp) + hf * 8 + cl);
+                const float* r = ref + ((size_t)(u / M) * L + l) * ref_dim;
+                if (ref_dim == 2) {
+                    px[hf] = __ldg(r) + o.x / (float)lv.W[l];
+                    py[hf] = __ldg(r + 1) + o.y / (float)lv.H[l];
+                } else {
+                    px[hf] = fmaf(o.x, (__ldg(r + 2) + __ldg(r + 3)) * 0.5f / (float)P, __ldg(r));
+                    py[hf] = fmaf(o.y, (__ldg(r + 4) + __ldg(r + 5)) * 0.5f / (float)P, __ldg(r + 1));
+                }
+            }
+        }
 
         // vals[] is stored pre-permuted so that after the butterfly lane `cl` owns outputs
         // j = i*LPU + cl (i = 0..PER-1): output j lives at position (j % LPU) * PER + j / LPU.
@@ -302,9 +373,24 @@ msda_bwd_vec_kernel(const float* __restrict__ value, const int64_t* __restrict__
             const float4 xy01 = ldg4(lp + l * 8);
             const float4 xy23 = ldg4(lp + l * 8 + 4);
             const float4 a4 = ldg4(ap + l * 4);
-            const float xs[4] = {xy01.x, xy01.z, xy23.x, xy23.z};
-            const float ys[4] = {xy01.y, xy01.w, xy23.y, xy23.w};
-            const float as[4] = {a4.x, a4.y, a4.z, a4.w};
+            float xs[4] = {xy01.x, xy01.z, xy23.x, xy23.z};
+            float ys[4] = {xy01.y, xy01.w, xy23.y, xy23.w};
+            float as[4] = {a4.x, a4.y, a4.z, a4.w};
+            if constexpr (FUSED) {
+                if (ref_dim == 2) {
+                    sc[l][0] = 1.f / (float)W; sc[l][1] = 1.f / (float)H;
+                } else {
+                    const float* r = ref + ((size_t)(u / M) * L + l) * ref_dim;
+                    sc[l][0] = (__ldg(r + 2) + __ldg(r + 3)) * 0.5f / (float)P;
+                    sc[l][1] = (__ldg(r + 4) + __ldg(r + 5)) * 0.5f / (float)P;
+                }
+#pragma unroll
+                for (int p = 0; p < P; ++p) {                      // point l * 4 + p lives in lane 4 (l & 1) + p, slot l / 2
+                    xs[p] = __shfl_sync(0xffffffffu, px[l >> 1], 4 * (l & 1) + p, 8);
+                    ys[p] = __shfl_sync(0xffffffffu, py[l >> 1], 4 * (l & 1) + p, 8);
+                    as[p] = __shfl_sync(0xffffffffu, pa[l >> 1], 4 * (l & 1) + p, 8);
+                }
+            }
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const float x = fmaf(xs[p], (float)W, -0.5f);
@@ -360,7 +446,22 @@ msda_bwd_vec_kernel(const float* __restrict__ value, const int64_t* __restrict__
                 }
             }
         }
-        if (live) {
+        if constexpr (FUSED) {
+            // lane cl owns d out / d loc entries j = 8 i + cl (level i, component cl & 1) and d out / d attn of points cl, 8 + cl
+            const float a0 = pa[0], a1 = pa[1];
+            float dot = a0 * vals[4] + a1 * vals[5];
+            dot += __shfl_xor_sync(0xffffffffu, dot, 4, 8);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 2, 8);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1, 8);
+            if (live) {
+                float* gl = grad_loc + (size_t)unit * NLOC;
+                float* gat = grad_attn + (size_t)unit * (L * P);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) gl[i * 8 + cl] = vals[i] * ((cl & 1) ? sc[i][1] : sc[i][0]);
+                gat[cl] = a0 * (vals[4] - dot);
+                gat[8 + cl] = a1 * (vals[5] - dot);
+            }
+        } else if (live) {
             float* gl = grad_loc + (size_t)unit * NLOC;
             float* gat = grad_attn + (size_t)unit * (L * P);
 #pragma unroll
@@ -536,7 +637,7 @@ int forward_impl(const T* value, const int64_t* shapes, const int64_t* lsi, cons
             if (lpu == 8 && L == 4 && use_old)
                 msda_fwd_vec_kernel<8, 4><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, S, M, L, Lq, n_units, upb, out);
             else if (lpu == 8 && L == 4)
-                msda_fwd_d32_kernel<<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, S, M, Lq, n_units, upb, out);
+                msda_fwd_d32_kernel<false><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, nullptr, 0, S, M, Lq, n_units, upb, out);
             else if (lpu == 8)
                 msda_fwd_vec_kernel<8, 0><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, S, M, L, Lq, n_units, upb, out);
             else if (lpu == 4)
@@ -617,6 +718,51 @@ int mdb_msda_backward_f32(const float* value, const int64_t* spatial_shapes, con
                           int M, int D, int L, int Lq, int P, float* grad_value, float* grad_loc, float* grad_attn,
                           void* stream) {
     return backward_impl<float>(value, spatial_shapes, level_start, sampling_loc, attn_weight, grad_out, B, S, M, D, L, Lq, P, grad_value, grad_loc, grad_attn, stream);
+}
+// Fused module path (MSDeformAttn.forward with constant reference points): pre-processing inside the sampling kernels.
+// D = 32, L = 4, P = 4 only (the model's configuration); anything else returns MDB_EUNSUPPORTED and the caller uses
+// mdb_msda_prep_* + mdb_msda_*.
+int mdb_msda_fused_forward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start, const float* offsets,
+                               const float* logits, const float* ref, int B, int S, int M, int D, int L, int Lq, int P, int ref_dim,
+                               float* out, void* stream_) {
+    if (D != 32 || L != 4 || P != 4 || (ref_dim != 2 && ref_dim != 6)) return MDB_EUNSUPPORTED;
+    int rc = check_common(value, spatial_shapes, level_start, offsets, logits, B, S, M, D, L, Lq, P);
+    if (rc) return rc;
+    const long long n_units = (long long)B * Lq * M;
+    if (n_units == 0) return 0;
+    if (!ref || !out) return MDB_EINVAL;
+    if (!aligned16(value) || !aligned16(offsets) || !aligned16(logits) || !aligned16(out)) return MDB_EUNSUPPORTED;
+    const int grid = grid_for((n_units + 3) / 4, 8);
+    const long long per = (kThreads / 32) * 4;
+    const long long upb = ((n_units + grid - 1) / grid + per - 1) / per * per;
+    msda_fwd_d32_kernel<true><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream_)>>>(value, spatial_shapes, level_start, offsets, logits, ref,
+                                                                                         ref_dim, S, M, Lq, n_units, upb, out);
+    return (int)cudaGetLastError();
+}
+int mdb_msda_fused_backward_f32(const float* value, const int64_t* spatial_shapes, const int64_t* level_start, const float* offsets,
+                                const float* logits, const float* ref, const float* grad_out, int B, int S, int M, int D, int L, int Lq,
+                                int P, int ref_dim, float* grad_value, float* grad_offsets, float* grad_logits, void* stream_) {
+    if (D != 32 || L != 4 || P != 4 || (ref_dim != 2 && ref_dim != 6)) return MDB_EUNSUPPORTED;
+    int rc = check_common(value, spatial_shapes, level_start, offsets, logits, B, S, M, D, L, Lq, P);
+    if (rc) return rc;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const long long n_units = (long long)B * Lq * M;
+    const size_t nv = (size_t)B * S * M * D;
+    if (!aligned16(value) || !aligned16(offsets) || !aligned16(logits) || !aligned16(grad_out) || !aligned16(grad_value))
+        return MDB_EUNSUPPORTED;
+    if (nv) {
+        if (!grad_value) return MDB_EINVAL;
+        cudaError_t e = cudaMemsetAsync(grad_value, 0, sizeof(float) * nv, stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (n_units == 0) return 0;
+    if (!ref || !grad_out || !grad_offsets || !grad_logits) return MDB_EINVAL;
+    const int grid = grid_for((n_units + 3) / 4, 6);
+    const long long per = (kThreads / 32) * 4;
+    const long long upb = ((n_units + grid - 1) / grid + per - 1) / per * per;
+    msda_bwd_vec_kernel<8, 4, true><<<grid, kThreads, 0, stream>>>(value, spatial_shapes, level_start, offsets, logits, grad_out, S, M, Lq, n_units,
+                                                                   upb, grad_value, grad_offsets, grad_logits, ref, ref_dim);
+    return (int)cudaGetLastError();
 }
 int mdb_msda_backward_f64(const double* value, const int64_t* spatial_shapes, const int64_t* level_start,
                           const double* sampling_loc, const double* attn_weight, const double* grad_out, int B, int S,

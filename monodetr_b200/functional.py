@@ -347,6 +347,53 @@ def msda_prep(off, logits, ref, spatial_shapes, M, L, P):
     return _MsdaPrep.apply(off, logits, ref, spatial_shapes, M, L, P)
 
 
+class _MsdaFused(Function):
+    """value (B,S,M,32), raw offsets (B,Lq,M*4*4*2), raw logits (B,Lq,M*16), constant reference points (B,Lq,4,rd) -> (B,Lq,M*32):
+    softmax / sampling-location pre-processing inside the sampling kernels (forward and backward)."""
+
+    @staticmethod
+    def forward(ctx, value, shapes, lsi, off, logits, ref):
+        value, off, logits = value.contiguous(), off.contiguous(), logits.contiguous()
+        refc = ref.detach().contiguous()
+        B, S, M, D = value.shape
+        Lq, rd = off.shape[1], refc.shape[-1]
+        out = torch.empty((B, Lq, M * D), dtype=torch.float32, device=value.device)
+        from . import msda as _m
+        if _m.PROBE is not None:        # bench.py: CUDA events tight around the launch (nothing else between them)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        _lib.check(_lib.lib().mdb_msda_fused_forward_f32(_p(value), _p(shapes), _p(lsi), _p(off), _p(logits), _p(refc), B, S, M, D, 4, Lq, 4, rd,
+                                                         _p(out), _s()), "msda_fused_forward")
+        if _m.PROBE is not None:
+            e1.record()
+            _m.PROBE.append((e0, e1, B, Lq))
+        _lib.count(1)
+        ctx.save_for_backward(value, shapes, lsi, off, logits, refc)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        value, shapes, lsi, off, logits, refc = ctx.saved_tensors
+        B, S, M, D = value.shape
+        Lq, rd = off.shape[1], refc.shape[-1]
+        dout = dout.contiguous()
+        gv, goff, glog = torch.empty_like(value), torch.empty_like(off), torch.empty_like(logits)
+        _lib.check(_lib.lib().mdb_msda_fused_backward_f32(_p(value), _p(shapes), _p(lsi), _p(off), _p(logits), _p(refc), _p(dout), B, S, M, D, 4, Lq,
+                                                          4, rd, _p(gv), _p(goff), _p(glog), _s()), "msda_fused_backward")
+        _lib.count(1)
+        return gv, None, None, goff, glog, None
+
+
+def msda_fused_applicable(value, ref, n_levels, n_points):
+    return (value.dtype == torch.float32 and value.shape[-1] == 32 and n_levels == 4 and n_points == 4 and not ref.requires_grad
+            and ref.shape[-1] in (2, 6) and not os.environ.get("MDB_MSDA_UNFUSED"))
+
+
+def msda_fused(value, spatial_shapes, level_start_index, off, logits, ref):
+    return _MsdaFused.apply(value, spatial_shapes, level_start_index, off, logits, ref)
+
+
 class _DepthSample(Function):
     """grid_sample(depth[:, None], xy[:, :, None], bilinear, zeros, align_corners=True) -> (B, N); xy is not differentiated."""
 

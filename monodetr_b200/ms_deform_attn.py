@@ -56,7 +56,13 @@ class MSDeformAttn(nn.Module):
             raise ValueError(f"Last dim of reference_points must be 2 or 6, but get {reference_points.shape[-1]} instead.")
         # :145-155 fused: softmax over the 16 (level, point) logits and loc = ref + off / (W_l, H_l)   [2-d refs]
         #                                                     or ref_xy + off / P * (l+r, t+b) / 2    [6-d refs]
-        sampling_locations, attention_weights = Fn.msda_prep(sampling_offsets, attention_logits, reference_points,
-                                                            input_spatial_shapes, self.n_heads, self.n_levels, self.n_points)
-        output = Fn.msda(value, input_spatial_shapes, input_level_start_index, sampling_locations, attention_weights)
+        if Fn.msda_fused_applicable(value, reference_points, self.n_levels, self.n_points):
+            # constant reference points (the encoder's pixel grid; decoder layers 1-2, whose boxes are detached): the
+            # pre-processing runs inside the sampling kernels
+            output = Fn.msda_fused(value, input_spatial_shapes, input_level_start_index, sampling_offsets, attention_logits,
+                                   reference_points)
+        else:
+            sampling_locations, attention_weights = Fn.msda_prep(sampling_offsets, attention_logits, reference_points,
+                                                                input_spatial_shapes, self.n_heads, self.n_levels, self.n_points)
+            output = Fn.msda(value, input_spatial_shapes, input_level_start_index, sampling_locations, attention_weights)
         return Fn.linear(output, self.output_proj.weight, self.output_proj.bias)

@@ -177,3 +177,35 @@ def test_full_size_properties():
     ref = (o1.double() * go.double()).sum()
     assert abs((ga.double() * a.double()).sum() - ref) <= 1e-5 * abs(ref) + 1e-2
     assert abs((gv.double() * v.double()).sum() - ref) <= 1e-4 * abs(ref) + 1e-1
+
+
+@pytest.mark.parametrize("Lq,rd,B", [(10200, 2, 2), (550, 6, 3), (53, 2, 1)])
+def test_fused_preprocessing_matches_the_two_step_path(Lq, rd, B):
+    """MSDeformAttn module path: softmax / sampling-location pre-processing INSIDE the sampling kernels
+    (mdb_msda_fused_*) against the separate pre-processing kernel + the op (both pinned above / in test_elementwise_gpu.py),
+    forward and the gradients wrt value, raw offsets and raw logits."""
+    from monodetr_b200 import functional as Fn
+    g = torch.Generator(device="cuda").manual_seed(Lq + rd)
+    shapes_t = torch.as_tensor(FULL_SHAPES, dtype=torch.long, device="cuda")
+    lsi = torch.cat((shapes_t.new_zeros((1,)), shapes_t.prod(1).cumsum(0)[:-1]))
+    S = int(shapes_t.prod(1).sum())
+    value = torch.randn(B, S, 8, 32, device="cuda", generator=g)
+    off = torch.randn(B, Lq, 8 * 4 * 4 * 2, device="cuda", generator=g) * 3
+    logits = torch.randn(B, Lq, 8 * 16, device="cuda", generator=g) * 2
+    ref = torch.rand(B, Lq, 4, rd, device="cuda", generator=g)
+    if rd == 6:
+        ref[..., 2:] *= 0.2
+    dout = torch.randn(B, Lq, 256, device="cuda", generator=g)
+    ins = [t.clone().requires_grad_() for t in (value, off, logits)]
+    assert Fn.msda_fused_applicable(ins[0], ref, 4, 4)
+    out = Fn.msda_fused(ins[0], shapes_t, lsi, ins[1], ins[2], ref)
+    gv, go, gl = torch.autograd.grad(out, ins, dout)
+    v2, o2, l2 = [t.clone().requires_grad_() for t in (value, off, logits)]
+    loc, attn = Fn.msda_prep(o2, l2, ref, shapes_t, 8, 4, 4)
+    ref_out = Fn.msda(v2, shapes_t, lsi, loc, attn)
+    rv, ro, rl = torch.autograd.grad(ref_out, (v2, o2, l2), dout)
+    _close(out, ref_out, 1e-5, 1e-6, "out")
+    _close(gv, rv, 2e-4, 2e-5, "grad_value")
+    _close(go, ro, 1e-4, 1e-5, "grad_offsets")
+    _close(gl, rl, 1e-4, 1e-5, "grad_logits")
+    assert not Fn.msda_fused_applicable(ins[0], ref.clone().requires_grad_(), 4, 4)      # boxes that need a gradient: two-step path
