@@ -249,6 +249,20 @@ int mdb_adamw_step_f32(float* p, const float* g, float* m, float* v, long long n
                        float one_minus_beta1, float beta2, float one_minus_beta2, float eps, float weight_decay,
                        float step_size, const float* step_size_dev, void* stream);
 
+/* ---- Inference post-process on the device (decode.cu) -- SURVEY.md 8 f3 ----
+ * extract: lib/helpers/decode_helper.py:57-110 (extract_dets_from_outputs).  logits (B,Q,C), boxes (B,Q,6) cx cy l r t b,
+ * dim3 (B,Q,3), depth (B,Q,2) [depth, log-variance], angle (B,Q,24).  dets (B,topk,37) = label, score, xs2d, ys2d, w, h, depth,
+ * heading[24], size3d[3], xs3d, ys3d, sigma; rows ordered by descending score, ties by ascending (query, class).
+ * Q*C <= 4096 (else MDB_EUNSUPPORTED), topk <= Q*C.
+ * decode: lib/helpers/decode_helper.py:8-54 (decode_detections) with the camera arithmetic of
+ * lib/datasets/kitti/kitti_utils.py:150-155,207-208,277-282.  img_size (B,2) [W,H], P2 (B,3,4), cls_mean_size (C,3).
+ * out (B,topk,14) = cls, alpha, x0, y0, x1, y1, h, w, l, X, Y, Z, ry, score*sigma for the count[b] leading rows whose score
+ * reaches `threshold` (the rest zero-filled); count (B) int32.  Both run on `stream` without synchronising. */
+int mdb_extract_dets_f32(const float* logits, const float* boxes, const float* dim3, const float* depth, const float* angle, int B,
+                         int Q, int C, int topk, float* dets, void* stream);
+int mdb_decode_dets_f32(const float* dets, const float* img_size, const float* P2, const float* cls_mean_size, int B, int topk, int C,
+                        float threshold, float* out, int* count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,11 @@ from . import functional as Fn
 
 
 class MSDeformAttn(nn.Module):
+    # Test switch (default off): treat the sampling locations as constants in backward.  d(bilinear)/d(location) is
+    # discontinuous at cell borders; with it frozen every remaining gradient of the model is smooth and can be held to a
+    # tight tolerance against the CPU oracle (tests/test_model_grad_gpu.py).
+    freeze_sampling_locations = False
+
     def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
         super().__init__()
         if d_model % n_heads != 0:
@@ -52,6 +57,8 @@ class MSDeformAttn(nn.Module):
         value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         sampling_offsets = Fn.linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias)
         attention_logits = Fn.linear(query, self.attention_weights.weight, self.attention_weights.bias)
+        if self.freeze_sampling_locations:
+            sampling_offsets, reference_points = sampling_offsets.detach(), reference_points.detach()
         if reference_points.shape[-1] not in (2, 6):
             raise ValueError(f"Last dim of reference_points must be 2 or 6, but get {reference_points.shape[-1]} instead.")
         # :145-155 fused: softmax over the 16 (level, point) logits and loc = ref + off / (W_l, H_l)   [2-d refs]

@@ -32,6 +32,19 @@ CFG = dict(num_classes=3, hidden_dim=256, nheads=8, enc_layers=3, dec_layers=3, 
 
 RESNET_LAYERS = [("layer1", 64, 3, 1), ("layer2", 128, 4, 2), ("layer3", 256, 6, 2), ("layer4", 512, 3, 2)]
 
+# Test switches (both default off = the reference's arithmetic, which is what the golden / reference pins check):
+#   FREEZE_SAMPLING  treat the MSDeformAttn sampling locations as constants in backward.  d(bilinear)/d(location) is
+#                    discontinuous at cell borders, so gradients THROUGH the locations amplify 1e-6 forward noise arbitrarily;
+#                    with the locations frozen every remaining gradient is a smooth function and can be compared tightly.
+#   DROPOUT_P        apply dropout with torch's RNG at the reference's 34 sites (depthaware_transformer.py:341-349,456-513,
+#                    depth_predictor/transformer.py:59-65) for STATISTICAL comparisons with the sm_100a path's hash masks.
+FREEZE_SAMPLING = False
+DROPOUT_P = 0.0
+
+
+def _drop(x):
+    return F.dropout(x, DROPOUT_P, training=True) if DROPOUT_P > 0 else x
+
 
 def inverse_sigmoid(x, eps=1e-5):       # utils/misc.py:473-477
     x = x.clamp(min=0, max=1)
@@ -89,8 +102,8 @@ def conv_gn(sd, p, x, stride=1, padding=0, relu=False):     # Sequential(Conv2d,
 
 def mha(sd, p, q, k, v, nheads=8):      # nn.MultiheadAttention forward, seq-first (L, B, E); returns attn output only
     out, _ = F.multi_head_attention_forward(
-        q, k, v, q.shape[-1], nheads, sd[p + ".in_proj_weight"], sd[p + ".in_proj_bias"], None, None, False, 0.0,
-        sd[p + ".out_proj.weight"], sd[p + ".out_proj.bias"], training=False, need_weights=False)
+        q, k, v, q.shape[-1], nheads, sd[p + ".in_proj_weight"], sd[p + ".in_proj_bias"], None, None, False, DROPOUT_P,
+        sd[p + ".out_proj.weight"], sd[p + ".out_proj.bias"], training=DROPOUT_P > 0, need_weights=False)
     return out
 
 
@@ -124,6 +137,8 @@ def ms_deform_attn(sd, p, query, reference_points, input_flatten, spatial_shapes
     else:   # 6-d (cx, cy, l, r, t, b): :154-155
         loc = reference_points[:, :, None, :, None, :2] + off / n_points * (
             reference_points[:, :, None, :, None, 2::2] + reference_points[:, :, None, :, None, 3::2]) * 0.5
+    if FREEZE_SAMPLING:
+        loc = loc.detach()
     out = msda_core_torch(value, spatial_shapes, loc, attn)
     return linear(sd, p + ".output_proj", out)
 
@@ -145,8 +160,8 @@ def depth_predictor(sd, srcs, pos1, cfg=CFG):           # depth_predictor.py:56-
     pos = pos1.flatten(2).permute(2, 0, 1)
     e = p + "depth_encoder.layers.0"
     qk = s + pos
-    s = layer_norm(sd, e + ".norm1", s + mha(sd, e + ".self_attn", qk, qk, s))
-    s = layer_norm(sd, e + ".norm2", s + linear(sd, e + ".linear2", F.relu(linear(sd, e + ".linear1", s))))
+    s = layer_norm(sd, e + ".norm1", s + _drop(mha(sd, e + ".self_attn", qk, qk, s)))
+    s = layer_norm(sd, e + ".norm2", s + _drop(linear(sd, e + ".linear2", _drop(F.relu(linear(sd, e + ".linear1", s))))))
     depth_embed = s.permute(1, 2, 0).reshape(B, C, H, W)
     d = weighted_depth.clamp(min=0, max=cfg["depth_max"])
     table = sd[p + "depth_pos_embed.weight"]
@@ -183,8 +198,8 @@ def transformer(sd, srcs, pos_embeds, query_embed, depth_pos_embed, training, cf
     for l in range(cfg["enc_layers"]):          # :345-354
         e = f"{p}encoder.layers.{l}"
         src2 = ms_deform_attn(sd, e + ".self_attn", memory + lvl_pos, ref_enc, memory, spatial_shapes)
-        memory = layer_norm(sd, e + ".norm1", memory + src2)
-        memory = layer_norm(sd, e + ".norm2", memory + linear(sd, e + ".linear2", F.relu(linear(sd, e + ".linear1", memory))))
+        memory = layer_norm(sd, e + ".norm1", memory + _drop(src2))
+        memory = layer_norm(sd, e + ".norm2", memory + _drop(linear(sd, e + ".linear2", _drop(F.relu(linear(sd, e + ".linear1", memory))))))
     c = memory.shape[-1]
     query_pos, tgt = torch.split(query_embed, c, dim=1)     # :283-287
     query_pos = query_pos.unsqueeze(0).expand(B, -1, -1)
@@ -199,7 +214,7 @@ def transformer(sd, srcs, pos_embeds, query_embed, depth_pos_embed, training, cf
         d = f"{p}decoder.layers.{l}"
         ref_in = reference_points[:, :, None].expand(-1, -1, len(shapes), -1)     # valid_ratios == 1
         tgt2 = mha(sd, d + ".cross_attn_depth", output.transpose(0, 1), dpe, dpe).transpose(0, 1)
-        t = layer_norm(sd, d + ".norm_depth", output + tgt2)
+        t = layer_norm(sd, d + ".norm_depth", output + _drop(tgt2))
         qk = t + query_pos
         q = (linear(sd, d + ".sa_qcontent_proj", qk) + linear(sd, d + ".sa_qpos_proj", qk)).transpose(0, 1)
         k = (linear(sd, d + ".sa_kcontent_proj", qk) + linear(sd, d + ".sa_kpos_proj", qk)).transpose(0, 1)
@@ -211,10 +226,10 @@ def transformer(sd, srcs, pos_embeds, query_embed, depth_pos_embed, training, cf
             v = torch.cat(v.split(nq // G, dim=0), dim=1)
         tgt2 = mha(sd, d + ".self_attn", q, k, v)
         tgt2 = torch.cat(tgt2.split(B, dim=1), dim=0).transpose(0, 1) if training else tgt2.transpose(0, 1)
-        t = layer_norm(sd, d + ".norm2", t + tgt2)
+        t = layer_norm(sd, d + ".norm2", t + _drop(tgt2))
         tgt2 = ms_deform_attn(sd, d + ".cross_attn", t + query_pos, ref_in, memory, spatial_shapes)
-        t = layer_norm(sd, d + ".norm1", t + tgt2)
-        output = layer_norm(sd, d + ".norm3", t + linear(sd, d + ".linear2", F.relu(linear(sd, d + ".linear1", t))))
+        t = layer_norm(sd, d + ".norm1", t + _drop(tgt2))
+        output = layer_norm(sd, d + ".norm3", t + _drop(linear(sd, d + ".linear2", _drop(F.relu(linear(sd, d + ".linear1", t))))))
         tmp = mlp(sd, f"bbox_embed.{l}", output, 3)         # :602-613
         if reference_points.shape[-1] == 6:
             new_ref = (tmp + inverse_sigmoid(reference_points)).sigmoid()

@@ -108,10 +108,10 @@ def test_backward_matches_oracle_gradients():
     worst.sort(reverse=True)
     print("worst gradient rel errs:", worst[:8], "median", sorted(rels)[len(rels) // 2])
     assert len(rels) > 250
-    # gradients through sampling locations are discontinuous in the inputs (see tests/test_oracle_model.py); TF32 noise
-    # moves a few samples across cell borders, so the tail is looser than the median.
-    assert sorted(rels)[len(rels) // 2] < 5e-3
-    assert worst[0][0] < 0.15, worst[:5]
+    # Bars from measurement (tests/test_model_grad_gpu.py, profiles/r02_gradient_parity.txt): medians 3e-4..1e-3; the tail (1e-2, query_embed 4.5e-2 through the decoder's sampling offsets) is ReLU / max-pool / sampling-cell selections flipping on forward noise, which an fp32
+    # CPU run shows against fp64 as well (5.5e-3).
+    assert sorted(rels)[len(rels) // 2] < 3e-3
+    assert worst[0][0] < 0.1, worst[:5]
 
 
 def test_train_step_with_dropout_runs_and_is_finite():
