@@ -263,6 +263,71 @@ int mdb_extract_dets_f32(const float* logits, const float* boxes, const float* d
 int mdb_decode_dets_f32(const float* dets, const float* img_size, const float* P2, const float* cls_mean_size, int B, int topk, int C,
                         float threshold, float* out, int* count, void* stream);
 
+/* ---- Training criterion on the device (criterion.cu) -- SURVEY.md 8 f1 ----
+ * lib/models/monodetr/matcher.py:36-104 (HungarianMatcher.forward), monodetr.py:297-532 (SetCriterion), depth_predictor/ddn_loss/
+ * {ddn_loss.py:43-127, balancer.py:21-81, focalloss.py:52-125}, lib/helpers/trainer_helper.py:175-186 (prepare_targets).
+ * Targets are the data loader's PADDED arrays (B, Gmax, ...) plus the validity mask (B, Gmax) -- no compaction on the host:
+ *   labels int32, boxes2d (cx cy w h), boxes3d (cx cy l r t b), depth, size3d (3), heading_bin int32, heading_res.
+ * Predictions are passed per decoder layer (layer 0 = the final outputs, then the aux outputs), L <= MDB_CRITERION_MAX_LAYERS:
+ *   logits (B,Q,C), boxes (B,Q,6), dim3 (B,Q,3), depth (B,Q,2), angle (B,Q,24), all contiguous fp32.
+ * Call order: prepare -> [all-reduce `total` across ranks] -> match -> depth_map -> losses; backward: depth_map (gradient mode) and
+ * losses_backward.  Nothing synchronises with the host.  Q / group <= 64, Gmax <= 64, B <= 1024 (else MDB_EUNSUPPORTED). */
+#define MDB_CRITERION_MAX_LAYERS 4
+#define MDB_CRITERION_NUM_LOSSES 10
+#define MDB_LOSS_CE 0           /* loss slots of one layer in `losses` / `grad_losses` (L, MDB_CRITERION_NUM_LOSSES) */
+#define MDB_LOSS_CLASS_ERROR 1  /* (logging only, no gradient) */
+#define MDB_LOSS_BBOX 2
+#define MDB_LOSS_GIOU 3
+#define MDB_LOSS_CARDINALITY 4  /* (logging only, no gradient) */
+#define MDB_LOSS_DEPTH 5
+#define MDB_LOSS_DIM 6
+#define MDB_LOSS_ANGLE 7
+#define MDB_LOSS_CENTER 8
+#define MDB_LOSS_DEPTH_MAP 9    /* layer 0 only */
+/* tlist (B,Gmax): indices of the valid targets of each image in their original order, -1 padded; count (B); total (1) = sum */
+int mdb_criterion_prepare(const unsigned char* mask, int B, int Gmax, int* tlist, int* count, float* total, void* stream);
+/* match (L,B,group,Gmax): query index in [0,Q) assigned to the j-th valid target of the image by the group's assignment problem
+ * (cost = w_bbox*L1(box) + w_center*L1(centre) + w_class*focal cost + w_giou*(-GIoU)), -1 where none; tclass (L,B,Q): class of
+ * the target a query is matched to, C for "no object". */
+int mdb_criterion_match_f32(int L, const float* const* logits, const float* const* boxes, const int* labels, const float* boxes3d,
+                            const int* tlist, const int* count, int B, int Q, int C, int group, int Gmax, float w_class, float w_center,
+                            float w_bbox, float w_giou, int* match, int* tclass, void* stream);
+/* Depth-map loss per pixel.  logits are addressed as logits[b*stride_b + pixel*stride_pix + c*stride_c], c in [0, num_bins]
+ * (NHWC: stride_pix = num_bins+1, stride_c = 1; NCHW: stride_pix = 1, stride_c = H*W).  boxes2d are scaled by (scale_x, scale_y)
+ * (the reference hard-codes 80, 24).  dlogits == NULL: writes pix_loss (B*H*W), already weighted fg/bg; otherwise writes
+ * dlogits (same addressing) = grad_loss[0] * d(mean-balanced loss)/d logits. */
+int mdb_criterion_depth_map_f32(const float* logits, long long stride_b, long long stride_pix, long long stride_c, const float* boxes2d,
+                                const float* depth, const int* tlist, const int* count, int B, int H, int W, int num_bins, int Gmax,
+                                float scale_x, float scale_y, float depth_min, float depth_max, float alpha, float fg_weight,
+                                float bg_weight, float* pix_loss, const float* grad_loss, float* dlogits, void* stream);
+/* losses (L, MDB_CRITERION_NUM_LOSSES), un-weighted, normalised by num_boxes = max(total * group / world_size, 1) as the reference.
+ * pix_loss / npix: output of the depth-map kernel (NULL / 0: slot stays 0).  aux (L): per-layer scalar kept for backward (the
+ * gradient-free compensation weight of the dimension loss, monodetr.py:414-416).  Deterministic (fixed-order reductions). */
+int mdb_criterion_losses_f32(int L, const float* const* logits, const float* const* boxes, const float* const* dim3,
+                             const float* const* depth, const float* const* angle, const int* labels, const float* boxes3d,
+                             const float* tdepth, const float* size3d, const int* hbin, const float* hres, const int* tlist,
+                             const int* count, const float* total, const int* match, const int* tclass, const float* pix_loss, int npix,
+                             int B, int Q, int C, int group, int Gmax, float focal_alpha, float world_size, float* losses, float* aux,
+                             void* stream);
+/* d(sum_k grad_losses[l][k] * losses[l][k]) / d predictions; every d* buffer is fully written (zeros for unmatched queries). */
+int mdb_criterion_losses_backward_f32(int L, const float* const* logits, const float* const* boxes, const float* const* dim3,
+                                      const float* const* depth, const float* const* angle, const int* labels, const float* boxes3d,
+                                      const float* tdepth, const float* size3d, const int* hbin, const float* hres, const int* tlist,
+                                      const int* count, const float* total, const int* match, const int* tclass, int B, int Q, int C,
+                                      int group, int Gmax, float focal_alpha, float world_size, const float* grad_losses,
+                                      const float* aux, float* const* dlogits, float* const* dboxes, float* const* ddim3, float* const* ddepth,
+                                      float* const* dangle, void* stream);
+
+/* ---- Input pipeline on the device (preprocess.cu) -- SURVEY.md 8 f4 ----
+ * lib/datasets/kitti/kitti_dataset.py:140-161: [flip] -> PIL Image.transform(AFFINE, BILINEAR) -> float32 / 255 -> (x - mean) / std -> CHW.
+ * src: DEVICE array of B device pointers to 8-bit RGB images (3 bytes per pixel), src_wh (B,2) [W,H] int32 and src_pitch (B) bytes
+ * per row (device); trans_inv (B,6) fp64 device = PIL's `data` (output pixel centre -> input coordinates, the reference's
+ * trans_inv); flip (B) bytes or NULL: sample the left-right mirrored image.  mean3 / std3: HOST floats.
+ * out (B,3,out_h,out_w) fp32.  The 8-bit interpolation result and the float conversion are bit-identical to PIL + numpy. */
+int mdb_warp_affine_normalize_u8(const unsigned char* const* src, const int* src_wh, const long long* src_pitch, const double* trans_inv,
+                                 const unsigned char* flip, int B, int out_w, int out_h, const float* mean3, const float* std3, float* out,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,12 @@ SIGNATURES = {
     "mdb_sum_mean_squares_forward_f32": [c_int, _PTR, _PTR, _PTR, _PTR],
     "mdb_sum_mean_squares_backward_f32": [c_int, _PTR, _PTR, _PTR, _PTR, _PTR],
     "mdb_adamw_step_f32": [_PTR] * 4 + [ctypes.c_longlong] * 2 + [c_float] * 7 + [_PTR, _PTR],
+    "mdb_criterion_prepare": [_PTR, c_int, c_int, _PTR, _PTR, _PTR, _PTR],
+    "mdb_criterion_match_f32": [c_int] + [_PTR] * 6 + [c_int] * 5 + [c_float] * 4 + [_PTR] * 3,
+    "mdb_criterion_depth_map_f32": [_PTR] + [ctypes.c_longlong] * 3 + [_PTR] * 4 + [c_int] * 5 + [c_float] * 7 + [_PTR] * 4,
+    "mdb_criterion_losses_f32": [c_int] + [_PTR] * 17 + [c_int] * 6 + [c_float] * 2 + [_PTR, _PTR, _PTR],
+    "mdb_criterion_losses_backward_f32": [c_int] + [_PTR] * 16 + [c_int] * 5 + [c_float] * 2 + [_PTR] * 8,
+    "mdb_warp_affine_normalize_u8": [_PTR] * 5 + [c_int] * 3 + [_PTR] * 4,
     "mdb_extract_dets_f32": [_PTR] * 5 + [c_int] * 4 + [_PTR, _PTR],
     "mdb_decode_dets_f32": [_PTR] * 4 + [c_int] * 3 + [c_float, _PTR, _PTR, _PTR],
 }

@@ -183,9 +183,10 @@ def _reference_criterion(cfg):
 
 def build(cfg, criterion_builder=None):
     """Same contract as the reference's build(cfg) (:550-614): returns (model, criterion).  The criterion (SetCriterion +
-    HungarianMatcher) is outside the hot path: `criterion_builder(cfg)` if given, else the reference's own
-    classes assembled as the reference does when `lib.models.monodetr` is importable (the situation inside
-    tools/train_val.py), else None (stand-alone use of the model, e.g. bench.py)."""
+    HungarianMatcher) is the step after the hot path: `criterion_builder(cfg)` if given; else, for a cfg
+    that carries the loss weights, the reference's own classes when `lib.models.monodetr` is importable (the situation
+    inside tools/train_val.py) unless cfg["criterion"] == "device", and otherwise this package's device-resident criterion
+    (monodetr_b200.criterion: same keys / values / gradients, no host synchronisation); None for a cfg without loss weights."""
     backbone = build_backbone(cfg)
     depthaware_transformer = build_depthaware_transformer(cfg)
     depth_predictor = DepthPredictor(cfg)
@@ -196,7 +197,10 @@ def build(cfg, criterion_builder=None):
     if criterion_builder is not None:
         criterion = criterion_builder(cfg)
     elif "cls_loss_coef" in cfg:                   # a full configs/monodetr.yaml model section (loss weights present)
-        criterion = _reference_criterion(cfg)
+        criterion = None if cfg.get("criterion") == "device" else _reference_criterion(cfg)
+        if criterion is None:
+            from .criterion import build_criterion
+            criterion = build_criterion(cfg).to(torch.device(cfg["device"]))
     else:
         criterion = None
     return model, criterion

@@ -32,7 +32,7 @@ def golden_dir():
 # Run order for `pytest -x`: the parity suites of the path's own operators first (MSDA, tensor-core conv/linear, whole
 # model), host/oracle checks next, everything else after -- so that one late failure cannot hide the main parity evidence.
 _ORDER = ["test_msda_gpu", "test_msda_reference_generators_gpu", "test_conv_gemm_gpu", "test_elementwise_gpu",
-          "test_attn_norm_gpu", "test_heads_gpu", "test_optim_gpu", "test_decode_gpu", "test_model_gpu", "test_model_grad_gpu"]
+          "test_attn_norm_gpu", "test_heads_gpu", "test_optim_gpu", "test_decode_gpu", "test_preprocess_gpu", "test_criterion_gpu", "test_model_gpu", "test_model_grad_gpu"]
 
 
 def _rank(item):
