@@ -368,6 +368,19 @@ def main():
                                    "e2e": b16["e2e"]["value"], "note": "same step at batch 16/GPU (the per-GPU batch of the N>1 runs): "
                                    "use this value, not `value`, as the 1-GPU point of a like-for-like scaling efficiency"}
             line["cpu_baseline"] = cpu_baseline_model()
+            if not args.batch and not os.environ.get("MDB_BENCH_NO_EXTRAS"):
+                # criterion / post-process / pre-process beside their CPU restatements, and the complete
+                # training iteration (forward + criterion + backward + AdamW) in one CUDA graph.  Extras, never the headline.
+                import gc
+                import bench_extras
+                gc.collect(); torch.cuda.empty_cache()
+                dev = torch.device("cuda", local_rank)
+                try:
+                    line["next_rows"] = bench_extras.next_rows_probe(dev)
+                    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+                    line["full_training_iteration"] = bench_extras.full_train_step_probe(dev, 8, args.steps, flush)
+                except Exception as e:
+                    line["extras_error"] = f"{type(e).__name__}: {e}"
     if line is not None:
         print(json.dumps(line), flush=True)
     if ws > 1:

@@ -95,92 +95,6 @@ def gemm_probe(dev, flush):
     return out
 
 
-def _timed(fn, iters=10, warm=3):
-    for _ in range(warm):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
-
-
-def next_rows_probe(dev):
-    """the steps either side of the hot path, each timed on the device (CUDA events, 10 calls) beside its CPU
-    restatement on the host (oracle/, the checker -- used here only as the reported baseline).  B = 8, KITTI-shaped inputs."""
-    import time
-    import numpy as np
-    from oracle import criterion as oc, decode as od, preprocess as op
-    from . import _lib
-    from .criterion import build_criterion
-    from .decode import decode_detections_device, extract_dets_from_outputs
-    from .preprocess import ImageBatchPreprocessor, get_affine_transform
-    res = {}
-    # f1: criterion (Hungarian matching + all losses), forward + backward of the weighted total
-    cfg = {"num_classes": 3, "cls_loss_coef": 2, "focal_alpha": 0.25, "bbox_loss_coef": 5, "giou_loss_coef": 2, "3dcenter_loss_coef": 10,
-           "dim_loss_coef": 1, "angle_loss_coef": 1, "depth_loss_coef": 1, "depth_map_loss_coef": 1, "set_cost_class": 2, "set_cost_bbox": 5,
-           "set_cost_giou": 2, "set_cost_3dcenter": 10, "aux_loss": True, "dec_layers": 3}
-    out, padded = oc.synthetic_case(5, 8, 550)
-    crit = build_criterion(cfg).to(dev).train()
-    o = {k: (v.to(dev).requires_grad_(True) if torch.is_tensor(v) else [{kk: vv.to(dev).requires_grad_(True) for kk, vv in a.items()} for a in v])
-         for k, v in out.items()}
-    tg = {k: v.to(dev) for k, v in padded.items()}
-
-    def crit_step():
-        losses = crit(o, tg)
-        sum(losses[k] * crit.weight_dict[k] for k in losses if k in crit.weight_dict).backward()
-    def crit_step_fused():
-        crit(o, tg)
-        crit.weighted_sum().backward()
-    n0 = _lib.launch_count()
-    ms = _timed(crit_step)
-    ms_fused = _timed(crit_step_fused)
-    t0 = time.perf_counter()
-    ro = {k: (v.clone().requires_grad_(True) if torch.is_tensor(v) else [{kk: vv.clone().requires_grad_(True) for kk, vv in a.items()} for a in v])
-          for k, v in out.items()}
-    rl, _ = oc.set_criterion(ro, padded, training=True)
-    w = oc.weight_dict()
-    sum(rl[k] * w[k] for k in rl if k in w).backward()
-    res["criterion"] = {"ms_fwd_bwd": ms_fused, "ms_fwd_bwd_dict_sum": ms, "own_kernel_launches": (_lib.launch_count() - n0) // 26, "host_syncs": 0,
-                        "cpu_port_ms": (time.perf_counter() - t0) * 1e3, "workload": "B=8, 550 queries x 3 decoder layers, 11 groups, <=12 objects/image; ms_fwd_bwd totals the loss with "
-                                    "SetCriterion.weighted_sum(), ms_fwd_bwd_dict_sum with the reference trainer's Python sum over the dict"}
-    # f3: post-process (top-k + decode), eval outputs of a batch of 32
-    h = od.synthetic_heads(3, 32, 50)
-    ho = {"pred_logits": torch.from_numpy(h["logits"]).to(dev), "pred_boxes": torch.from_numpy(h["boxes"]).to(dev),
-          "pred_3d_dim": torch.from_numpy(h["dim3"]).to(dev), "pred_depth": torch.from_numpy(h["depth"]).to(dev),
-          "pred_angle": torch.from_numpy(h["angle"]).to(dev)}
-    sz, P2, ms3 = torch.from_numpy(h["img_size"]).to(dev), torch.from_numpy(h["P2"]).to(dev), torch.from_numpy(h["mean_size"]).to(dev)
-    ms = _timed(lambda: decode_detections_device(extract_dets_from_outputs(ho, topk=50), sz, P2, ms3, 0.2))
-    t0 = time.perf_counter()
-    od.decode_dets(od.extract_dets(h["logits"], h["boxes"], h["dim3"], h["depth"], h["angle"], 50), h["img_size"], h["P2"], h["mean_size"], 0.2)
-    res["postprocess"] = {"ms": ms, "cpu_port_ms": (time.perf_counter() - t0) * 1e3, "workload": "B=32, 50 queries x 3 classes, top-50, threshold 0.2"}
-    # f4: warp + normalise 8 KITTI-sized frames to 1280x384 (sources already on the device)
-    sizes = [(1242, 375), (1224, 370), (1238, 374), (1241, 376)] * 2
-    imgs = op.synthetic_images(1, sizes)
-    tinv = np.stack([get_affine_transform(np.array(s, np.float64) / 2, np.array(s, np.float64), 0, np.array([1280, 384]), inv=1)[1] for s in sizes])
-    src = [torch.from_numpy(im).to(dev) for im in imgs]
-    pre = ImageBatchPreprocessor((1280, 384), device=dev)
-    ms = _timed(lambda: pre(src, tinv))
-    nbytes = 8 * 3 * 384 * 1280 * 4 + sum(w * hh * 3 for w, hh in sizes)
-    t0 = time.perf_counter()
-    try:
-        from PIL import Image
-        for im, t in zip(imgs, tinv):
-            x = np.array(Image.fromarray(im).transform((1280, 384), method=Image.AFFINE, data=tuple(t.reshape(-1).tolist()), resample=Image.BILINEAR))
-            op.normalize(x)
-        kind = "PIL + numpy (the reference's calls), 1 thread"
-    except ImportError:
-        for im, t in zip(imgs, tinv):
-            op.preprocess(im, t.reshape(-1), (1280, 384))
-        kind = "numpy port, 1 thread"
-    res["preprocess"] = {"ms": ms, "GBps": nbytes / (ms * 1e-3) / 1e9, "cpu_ms": (time.perf_counter() - t0) * 1e3, "cpu_kind": kind,
-                         "workload": "8 frames ~1242x375 u8 -> (8,3,384,1280) fp32"}
-    return res
-
-
 def run(args, rank, local_rank, ws, infer=False, batch_override=None, extras=True):
     """infer=False: BASELINE configs[2]/[3] (train step).  infer=True: configs[4], eval-mode forward only, batch 32,
     no gradients, N>1 = independent replicas (no collective)."""
@@ -346,7 +260,6 @@ def run(args, rank, local_rank, ws, infer=False, batch_override=None, extras=Tru
             enc_ms = probe.encoder_ms()
     loss_val = float(loss_buf.item())
     gemm = gemm_probe(dev, flush) if (extras and rank == 0 and not infer) else None
-    nxt = next_rows_probe(dev) if (extras and rank == 0 and not infer and ws == 1) else None
 
     if rank != 0:
         return None
@@ -378,8 +291,6 @@ def run(args, rank, local_rank, ws, infer=False, batch_override=None, extras=Tru
     }
     if allreduce_ms is not None:
         line["allreduce_ms_exposed"] = allreduce_ms
-    if nxt:
-        line["next_rows"] = nxt
     if gemm:
         best = max(gemm, key=lambda c: c["tflops"])
         line["roofline_gemm"] = {"kernel": "tc_conv_gemm_kernel (tcgen05 BF16x3 implicit GEMM; " + best["shape"] + ")", "bound": "tensor",

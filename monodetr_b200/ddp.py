@@ -22,6 +22,8 @@ class FlatGradBucket:
     at the reduced views, so an optimizer stepping on `p.grad` always sees the rank-mean gradients.  The captured
     tensors are remembered separately, so re-pointing `.grad` never changes what the next replay's pack reads."""
 
+    ALIGN = 32
+
     def __init__(self, model, views=False):
         named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and not any(s in n for s in _NEVER_USED)]
         # Bucket order = weight-decay tensors first, then the tensors with 'bias' in their name (the reference's optimizer
@@ -30,15 +32,20 @@ class FlatGradBucket:
         named = [(n, p) for n, p in named if "bias" not in n] + [(n, p) for n, p in named if "bias" in n]
         self.names = [n for n, _ in named]
         self.params = [p for _, p in named]
-        self.n_decay = sum(p.numel() for n, p in named if "bias" not in n)
-        n = sum(p.numel() for p in self.params)
+        # Every tensor starts on a 128-byte boundary of the flat buffer (ALIGN elements): the fused AdamW turns the parameters
+        # themselves into views at the same offsets, and the kernels read parameters with 16-byte vector loads and TMA.  The
+        # padding elements stay zero in every flat buffer (zero gradient -> zero moments -> zero update).
+        self.offsets, off = [], 0
+        for _, p in named:
+            self.offsets.append(off)
+            off += -(-p.numel() // self.ALIGN) * self.ALIGN
+        n_bias = sum(1 for n, _ in named if "bias" in n)
+        self.n_decay = self.offsets[len(named) - n_bias] if n_bias else off      # elements [0, n_decay) get weight decay
+        self.param_numel = sum(p.numel() for p in self.params)
         dev = self.params[0].device
-        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.views, off = [], 0
-        for p in self.params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
-        self.numel = n
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(self.offsets, self.params)]
+        self.numel = off                             # length of the flat buffers (incl. alignment padding)
         self.use_views = views
         self.static_grads = None     # CUDA-graph mode: the gradient tensors the captured backward writes every replay
         if views:

@@ -34,14 +34,12 @@ class FusedAdamW(torch.optim.Optimizer):
         groups = [{"params": b.params[nd:], "weight_decay": 0}, {"params": b.params[:nd], "weight_decay": weight_decay}]
         super().__init__([g for g in groups if g["params"]], dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False))
         # parameters -> views of one flat buffer, in bucket order
-        self.flat_p = torch.empty_like(b.flat)
-        off = 0
+        self.flat_p = torch.zeros_like(b.flat)
         with torch.no_grad():
-            for p in b.params:
+            for off, p in zip(b.offsets, b.params):          # 128-byte aligned offsets: vector loads / TMA on parameters keep working
                 v = self.flat_p[off:off + p.numel()].view_as(p)
                 v.copy_(p)
                 p.data = v
-                off += p.numel()
         self.exp_avg = torch.zeros_like(b.flat)
         self.exp_avg_sq = torch.zeros_like(b.flat)
         self.step_count = 0

@@ -21,7 +21,8 @@ def _worker(rank, world, store_path, q, views):
     broadcast_parameters(model)
     w0 = model["a"].weight.detach().clone()
     bucket = FlatGradBucket(model, views=views)
-    assert bucket.numel == sum(p.numel() for n, p in model.named_parameters() if "sa_v_proj" not in n)
+    assert bucket.param_numel == sum(p.numel() for n, p in model.named_parameters() if "sa_v_proj" not in n)
+    assert bucket.numel >= bucket.param_numel and all(o % bucket.ALIGN == 0 for o in bucket.offsets)
     assert model["sa_v_proj"].weight.grad is None
     bucket.zero()
     x = torch.full((3, 8), float(rank + 1))
@@ -32,7 +33,8 @@ def _worker(rank, world, store_path, q, views):
     gathered = [torch.zeros_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
     expect = sum(gathered) / world
-    ok = torch.allclose(bucket.flat, expect, atol=1e-6) and model["a"].weight.grad.data_ptr() == bucket.flat.data_ptr()
+    reduced = torch.cat([v.reshape(-1) for v in bucket.views])          # (the flat buffer also holds alignment padding)
+    ok = torch.allclose(reduced, expect, atol=1e-6) and model["a"].weight.grad.data_ptr() == bucket.flat.data_ptr()
     if not views:
         # CUDA-graph mode: a "replay" rewrites the captured gradient tensors in place; after all_reduce() an optimizer
         # reading p.grad must see the rank mean, and the captured sources must stay what the next replay writes

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 def _toy():
     torch.manual_seed(0)
     m = torch.nn.ModuleDict({
-        "a": torch.nn.Linear(37, 19),            # odd sizes: tensors start at unaligned offsets of the flat buffer
+        "a": torch.nn.Linear(37, 19),            # odd sizes: alignment padding between the tensors of the flat buffer
         "norm": torch.nn.LayerNorm(19),
         "b": torch.nn.Linear(19, 3),
         "emb": torch.nn.Embedding(11, 5),
@@ -37,12 +37,14 @@ def _check(params, names, opt, steps, lr, wd):
         for p, r, n in zip(params, ref, names):
             assert torch.allclose(p.detach(), r, rtol=4e-7, atol=1e-9), (n, step, float((p.detach() - r).abs().max()))
             exact = exact and torch.equal(p.detach(), r)
-    off = 0
-    for m_ref, v_ref in zip(ms, vs):
+    for off, m_ref, v_ref in zip(opt.bucket.offsets, ms, vs):
         n = m_ref.numel()
         assert torch.allclose(opt.exp_avg[off:off + n].view_as(m_ref), m_ref, rtol=4e-7, atol=1e-12)
         assert torch.allclose(opt.exp_avg_sq[off:off + n].view_as(v_ref), v_ref, rtol=4e-7, atol=1e-12)
-        off += n
+    used = torch.zeros(opt.bucket.numel, dtype=torch.bool, device="cuda")
+    for off, p in zip(opt.bucket.offsets, params):
+        used[off:off + p.numel()] = True
+    assert not opt.flat_p[~used].any() and not opt.exp_avg[~used].any() and not opt.exp_avg_sq[~used].any()     # padding stays zero
     print("bit-exact vs torch's kernels:", exact)
 
 
@@ -58,7 +60,8 @@ def test_fused_adamw_matches_reference_update(device_step):
         assert torch.equal(p.detach(), before[n])
         assert opt.flat_p.data_ptr() <= p.data_ptr() < opt.flat_p.data_ptr() + opt.flat_p.numel() * 4
     assert bucket.names[:bucket.names.index("a.bias")] == [n for n in bucket.names if "bias" not in n]   # decay tensors first
-    assert bucket.n_decay == sum(p.numel() for n, p in model.named_parameters() if "bias" not in n)
+    assert bucket.n_decay == bucket.offsets[bucket.names.index("a.bias")] and all(o % 32 == 0 for o in bucket.offsets)
+    assert all(p.data_ptr() % 128 == 0 for p in bucket.params)
     _check(bucket.params, bucket.names, opt, 6, 2e-4, 1e-4)
 
 
@@ -73,9 +76,21 @@ def test_fused_adamw_on_the_model():
     opt = build_optimizer({"type": "adamw", "lr": 2e-4, "weight_decay": 1e-4}, model)
     assert list(model.state_dict().keys()) == keys
     b = opt.bucket
-    assert len(b.params) == 313 and b.numel == 37056453        # gradient-receiving tensors
+    assert len(b.params) == 313 and b.param_numel == 37056453  # gradient-receiving tensors
     untouched = {n: p.detach().clone() for n, p in model.named_parameters() if all(p is not q for q in b.params)}
     _check(b.params, b.names, opt, 2, 2e-4, 1e-4)
     for n, p in model.named_parameters():                       # never-used / frozen tensors are not updated (optimizer_helper.py:95-96)
         if n in untouched:
             assert torch.equal(p.detach(), untouched[n]), n
+    # the model still runs on the flattened parameters (every tensor 128-byte aligned) and trains
+    from oracle import monodetr_torch as om
+    images, calibs, sizes = om.synthetic_inputs(1, 3, H=192, W=640)
+    model.train()
+    for _ in range(2):
+        opt.zero_grad()
+        out = model(images.cuda(), calibs.cuda(), None, sizes.cuda())
+        loss = om.surrogate_loss(out)
+        loss.backward()
+        opt.step()
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss) and all(torch.isfinite(p).all() for p in b.params)
