@@ -240,7 +240,8 @@ class DepthAwareTransformer(nn.Module):
             cache[key] = (ss, torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1])))
         return cache[key]
 
-    def forward(self, srcs, masks, pos_embeds, query_embed=None, depth_pos_embed=None, depth_pos_embed_ip=None, attn_mask=None):
+    def forward(self, srcs, masks, pos_embeds, query_embed=None, depth_pos_embed=None, depth_pos_embed_ip=None, attn_mask=None,
+                before_decoder=None):
         """srcs: list of NHWC maps (B, H_l, W_l, C); masks: None (all-False) or list of (B, H_l, W_l) bool;
         pos_embeds: list of (H_l*W_l, C); query_embed (nq, 2C); depth_pos_embed (B, HW1, C).
         Returns hs (L, B, nq, C), init_reference (B, nq, 2), inter_references (L, B, nq, 6), inter_dims (L, B, nq, 3),
@@ -262,6 +263,8 @@ class DepthAwareTransformer(nn.Module):
         tgt = tgt.unsqueeze(0).expand(B, -1, -1).contiguous()
         reference_points = Fn.linear(query_pos.contiguous(), self.reference_points.weight, self.reference_points.bias).sigmoid()
         init_reference_out = reference_points
+        if before_decoder is not None:           # (the depth predictor may still be running on its own stream: join it here)
+            before_decoder()
         hs, inter_references, inter_dims, boxes = self.decoder(tgt, reference_points, memory, spatial_shapes, level_start_index,
                                                               query_pos, mask_flatten, depth_pos_embed, None, bs=B)
         return hs, init_reference_out, inter_references, inter_dims, boxes

@@ -52,6 +52,45 @@ class _Fork:
                 t.record_stream(self.main)
 
 
+_BRANCH_STREAMS = {}
+_BRANCHES = not os.environ.get("MDB_NO_BRANCH_STREAMS")
+
+
+class Branch:
+    """Run an independent part of the forward graph on its own stream (`with Branch(i): ...`, then `.join(*outputs)` on the
+    consumer side).  Autograd replays every node's backward on the stream its forward ran on, so the backward of the branch
+    overlaps too; inside a CUDA-graph capture this is the ordinary fork / join.  `MDB_NO_BRANCH_STREAMS=1` makes it a no-op."""
+
+    def __init__(self, index):
+        self.main = torch.cuda.current_stream()
+        self.side = None
+        if _BRANCHES:
+            key = (torch.cuda.current_device(), index)
+            self.side = _BRANCH_STREAMS.get(key)
+            if self.side is None:
+                self.side = _BRANCH_STREAMS[key] = torch.cuda.Stream(key[0])
+        self._ctx = None
+
+    def __enter__(self):
+        if self.side is not None:
+            self.side.wait_stream(self.main)
+            self._ctx = torch.cuda.stream(self.side)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            self._ctx.__exit__(*exc)
+        return False
+
+    def join(self, *tensors):
+        if self.side is not None:
+            self.main.wait_stream(self.side)
+            for t in tensors:                  # allocated on the branch stream, consumed (and possibly freed) on the main one
+                if t is not None:
+                    t.record_stream(self.main)
+
+
 # ---- small raw wrappers ---------------------------------------------------------------------------------
 def relu_backward(dy, y, scale=1.0):
     dy = dy.contiguous()

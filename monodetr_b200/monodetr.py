@@ -122,25 +122,37 @@ class MonoDETR(nn.Module):
             pos.append(self.backbone[1](src))
         query_embeds = self.query_embed.weight if self.training else self.query_embed.weight[:self.num_queries]
 
-        depth_logits, depth_pos_embed, weighted_depth, depth_pos_embed_ip = self.depth_predictor(srcs, None, pos[1])
+        # The depth predictor and the visual encoder both depend on `srcs` only: the (small) depth branch runs on its own
+        # stream beside the encoder and is joined right before the decoder, its first consumer.
+        depth_branch = Fn.Branch(0)
+        with depth_branch:
+            depth_logits, depth_pos_embed, weighted_depth, depth_pos_embed_ip = self.depth_predictor(srcs, None, pos[1])
         hs, init_reference, inter_references, inter_references_dim, boxes = self.depthaware_transformer(
-            srcs, None, pos, query_embeds, depth_pos_embed, depth_pos_embed_ip)
+            srcs, None, pos, query_embeds, depth_pos_embed, depth_pos_embed_ip,
+            before_decoder=lambda: depth_branch.join(depth_logits, depth_pos_embed, weighted_depth, depth_pos_embed_ip))
 
         outputs_coords, outputs_classes, outputs_3d_dims, outputs_depths, outputs_angles = [], [], [], [], []
+        branches = []
         for lvl in range(hs.shape[0]):
-            # The reference re-evaluates bbox_embed[lvl](hs[lvl]) + inverse_sigmoid(reference) here (:216-228); that is the
-            # very tensor the decoder already formed before detaching it, so it is reused (same values, same gradients).
-            outputs_coord = boxes[lvl]
-            outputs_coords.append(outputs_coord)
-            cls = self.class_embed[lvl]
-            outputs_classes.append(Fn.linear(hs[lvl], cls.weight, cls.bias))
-            size3d = inter_references_dim[lvl]
-            outputs_3d_dims.append(size3d)
-            depth_reg = self.depth_embed[lvl](hs[lvl])
-            # regressed + geometric + depth-map depth, averaged (:230-262; the sample grid uses detached centres): one kernel
-            depth_ave = Fn.head_depth(outputs_coord, size3d, depth_reg, weighted_depth, calibs, img_sizes)
-            outputs_depths.append(depth_ave)
-            outputs_angles.append(self.angle_embed[lvl](hs[lvl]))
+            # The heads of the three decoder levels are independent chains of small GEMMs (launch-latency bound): one stream each.
+            br = Fn.Branch(1 + lvl)
+            with br:
+                # The reference re-evaluates bbox_embed[lvl](hs[lvl]) + inverse_sigmoid(reference) here (:216-228); that is the
+                # very tensor the decoder already formed before detaching it, so it is reused (same values, same gradients).
+                outputs_coord = boxes[lvl]
+                outputs_coords.append(outputs_coord)
+                cls = self.class_embed[lvl]
+                outputs_classes.append(Fn.linear(hs[lvl], cls.weight, cls.bias))
+                size3d = inter_references_dim[lvl]
+                outputs_3d_dims.append(size3d)
+                depth_reg = self.depth_embed[lvl](hs[lvl])
+                # regressed + geometric + depth-map depth, averaged (:230-262; the sample grid uses detached centres): one kernel
+                depth_ave = Fn.head_depth(outputs_coord, size3d, depth_reg, weighted_depth, calibs, img_sizes)
+                outputs_depths.append(depth_ave)
+                outputs_angles.append(self.angle_embed[lvl](hs[lvl]))
+            branches.append(br)
+        for lvl, br in enumerate(branches):
+            br.join(outputs_classes[lvl], outputs_depths[lvl], outputs_angles[lvl])
 
         out = {"pred_logits": outputs_classes[-1], "pred_boxes": outputs_coords[-1], "pred_3d_dim": outputs_3d_dims[-1],
                "pred_depth": outputs_depths[-1], "pred_angle": outputs_angles[-1],
