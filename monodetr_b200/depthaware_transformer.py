@@ -120,16 +120,26 @@ class DepthAwareDecoderLayer(nn.Module):
         self.nhead = n_heads
         self.site_base = 0
 
+    def depth_kv(self, depth_pos_embed):
+        """Key / value projection of the depth cross attention (one GEMM): a function of the depth embedding only."""
+        a = self.cross_attn_depth
+        c = a.embed_dim
+        return Fn.linear(depth_pos_embed, a.in_proj_weight[c:], a.in_proj_bias[c:])
+
     def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, level_start_index, src_padding_mask,
-                depth_pos_embed, mask_depth, bs):
-        """tgt/query_pos (B, nq, C); src (B, S, C); depth_pos_embed (B, 1920, C) batch-first."""
+                depth_pos_embed, mask_depth, bs, ahead=None):
+        """tgt/query_pos (B, nq, C); src (B, S, C); depth_pos_embed (B, 1920, C) batch-first.
+        `ahead`: optional dict of work the decoder started on branch streams -- "kv" / "value" (callables returning the depth
+        key-value projection / the projected memory once joined) and "reference_points" (callable returning the boxes of the
+        previous layer, needed only by the deformable cross attention)."""
         sb = self.site_base
         c = tgt.shape[-1]
         B, nq, _ = tgt.shape
+        ahead = ahead or {}
         # ---- depth cross attention (:456-462): q = tgt (no positional term), k = v = depth_pos_embed -------------
         a = self.cross_attn_depth
         q = Fn.linear(tgt, a.in_proj_weight[:c], a.in_proj_bias[:c])
-        kv = Fn.linear(depth_pos_embed, a.in_proj_weight[c:], a.in_proj_bias[c:])                     # fused k,v projection
+        kv = ahead["kv"]() if "kv" in ahead else self.depth_kv(depth_pos_embed)                     # fused k,v projection
         o = Fn.attention(q, kv[..., :c], kv[..., c:], mask_depth, a.dropout, self.training, sb)
         tgt2 = Fn.linear(o, a.out_proj.weight, a.out_proj.bias)
         tgt = Fn.add_layernorm(tgt, tgt2, self.norm_depth.weight, self.norm_depth.bias, self.norm_depth.eps,
@@ -137,12 +147,18 @@ class DepthAwareDecoderLayer(nn.Module):
         # ---- (group-wise) self attention (:465-503) ------------------------------------------------------------------
         qk = tgt + query_pos
         # q_content + q_pos are two linears of the SAME input: one GEMM with the summed weights (:467-473)
-        qs = Fn.linear(qk, self.sa_qcontent_proj.weight + self.sa_qpos_proj.weight, self.sa_qcontent_proj.bias + self.sa_qpos_proj.bias)
-        ks = Fn.linear(qk, self.sa_kcontent_proj.weight + self.sa_kpos_proj.weight, self.sa_kcontent_proj.bias + self.sa_kpos_proj.bias)
         s = self.self_attn
+        # the key chain and the value projection do not depend on the query chain: three streams, two GEMMs deep instead of five
+        br_k, br_v = Fn.Branch(7, level=2), Fn.Branch(8, level=2)
+        with br_k:
+            ks = Fn.linear(qk, self.sa_kcontent_proj.weight + self.sa_kpos_proj.weight, self.sa_kcontent_proj.bias + self.sa_kpos_proj.bias)
+            k = Fn.linear(ks, s.in_proj_weight[c:2 * c], s.in_proj_bias[c:2 * c])
+        with br_v:
+            v = Fn.linear(tgt, s.in_proj_weight[2 * c:], s.in_proj_bias[2 * c:])                      # v = tgt (:477)
+        qs = Fn.linear(qk, self.sa_qcontent_proj.weight + self.sa_qpos_proj.weight, self.sa_qcontent_proj.bias + self.sa_qpos_proj.bias)
         q = Fn.linear(qs, s.in_proj_weight[:c], s.in_proj_bias[:c])
-        k = Fn.linear(ks, s.in_proj_weight[c:2 * c], s.in_proj_bias[c:2 * c])
-        v = Fn.linear(tgt, s.in_proj_weight[2 * c:], s.in_proj_bias[2 * c:])                          # v = tgt (:477)
+        br_k.join(k)
+        br_v.join(v)
         if self.training:
             # 11 groups of 50 queries attend only within their group (:480-494): fold groups into the batch (a view)
             g = self.group_num
@@ -154,7 +170,10 @@ class DepthAwareDecoderLayer(nn.Module):
         tgt2 = Fn.linear(o, s.out_proj.weight, s.out_proj.bias)
         tgt = Fn.add_layernorm(tgt, tgt2, self.norm2.weight, self.norm2.bias, self.norm2.eps, self.dropout2.p, self.training, sb + 3)
         # ---- deformable cross attention over the image memory (:506-510) ---------------------------------------------
-        tgt2 = self.cross_attn(tgt + query_pos, reference_points, src, src_spatial_shapes, level_start_index, src_padding_mask)
+        if "reference_points" in ahead:
+            reference_points = ahead["reference_points"]()
+        tgt2 = self.cross_attn(tgt + query_pos, reference_points, src, src_spatial_shapes, level_start_index, src_padding_mask,
+                               value=ahead["value"]() if "value" in ahead else None)
         tgt = Fn.add_layernorm(tgt, tgt2, self.norm1.weight, self.norm1.bias, self.norm1.eps, self.dropout1.p, self.training, sb + 4)
         # ---- ffn (:431-435) ----------------------------------------------------------------------------------------------
         h = Fn.linear(tgt, self.linear1.weight, self.linear1.bias, relu=True)
@@ -184,20 +203,58 @@ class DepthAwareDecoder(nn.Module):
         output = tgt
         n_levels = src_spatial_shapes.shape[0]
         intermediate, intermediate_boxes, intermediate_refs, intermediate_dims = [], [], [], []
+        # Work that depends on the memory / the depth embedding only is started now on branch streams and joined where each layer
+        # first needs it: the depth key-value projections (3 GEMMs) and the deformable attention's value projections (3 large
+        # GEMMs that fill the SMs the decoder's small launches leave idle).
+        ahead_kv, ahead_val = [], []
         for lid, layer in enumerate(self.layers):
-            # valid_ratios == 1 (all-False masks): reference_points_input is a broadcast over levels (:565-571)
-            reference_points_input = reference_points[:, :, None].expand(-1, -1, n_levels, -1)
-            output = layer(output, query_pos, reference_points_input, src, src_spatial_shapes, src_level_start_index,
-                           src_padding_mask, depth_pos_embed, mask_depth, bs)
-            tmp = self.bbox_embed[lid](output)                                   # :602-613
-            # (tmp + inverse_sigmoid(ref)).sigmoid() on the first 2 / all 6 components: one fused kernel
-            new_reference_points = Fn.box_refine(tmp, reference_points)
+            bk, bv = Fn.Branch(9 + lid, level=2), Fn.Branch(12 + lid, level=2)
+            with bk:
+                kv = layer.depth_kv(depth_pos_embed)
+            with bv:
+                val = layer.cross_attn.project_value(src, src_padding_mask)
+            ahead_kv.append((bk, kv))
+            ahead_val.append((bv, val))
+
+        def joined(pair):
+            def get():
+                pair[0].join(pair[1])
+                return pair[1]
+            return get
+
+        box_branch = None                       # (branch, boxes) of the previous layer: joined right before its first use
+        dim_branches = []
+        for lid, layer in enumerate(self.layers):
+            ahead = {"kv": joined(ahead_kv[lid]), "value": joined(ahead_val[lid])}
+            if box_branch is None:
+                ref_in = reference_points[:, :, None].expand(-1, -1, n_levels, -1)   # valid_ratios == 1 (:565-571): broadcast over levels
+            else:
+                ref_in = None
+                ahead["reference_points"] = (lambda bb: lambda: (bb[0].join(bb[1]), bb[1].detach()[:, :, None].expand(-1, -1, n_levels, -1))[1])(box_branch)
+            output = layer(output, query_pos, ref_in, src, src_spatial_shapes, src_level_start_index,
+                           src_padding_mask, depth_pos_embed, mask_depth, bs, ahead=ahead)
+            if box_branch is not None:
+                reference_points = box_branch[1].detach()                       # (joined inside the layer)
+                intermediate_refs.append(reference_points)
+            # box refinement (:602-613) and the size head read this layer's output but the next layer needs the boxes only at its
+            # deformable cross attention: both leave the critical path
+            bb = Fn.Branch(5, level=2)
+            with bb:
+                tmp = self.bbox_embed[lid](output)
+                # (tmp + inverse_sigmoid(ref)).sigmoid() on the first 2 / all 6 components: one fused kernel
+                new_reference_points = Fn.box_refine(tmp, reference_points)
+            box_branch = (bb, new_reference_points)
+            bd = Fn.Branch(6, level=2)
+            with bd:
+                reference_dims = self.dim_embed[lid](output)
+            dim_branches.append((bd, reference_dims))
             intermediate_boxes.append(new_reference_points)                     # with gradient: == outputs_coord of monodetr.py:216-228
-            reference_points = new_reference_points.detach()
-            reference_dims = self.dim_embed[lid](output)
             intermediate.append(output)
-            intermediate_refs.append(reference_points)
             intermediate_dims.append(reference_dims)
+        box_branch[0].join(box_branch[1])
+        intermediate_refs.append(box_branch[1].detach())
+        for bd, dims in dim_branches:
+            bd.join(dims)
         return torch.stack(intermediate), torch.stack(intermediate_refs), torch.stack(intermediate_dims), intermediate_boxes
 
 

@@ -54,6 +54,9 @@ class _Fork:
 
 _BRANCH_STREAMS = {}
 _BRANCHES = not os.environ.get("MDB_NO_BRANCH_STREAMS")
+# level 1: depth predictor beside the encoder, the three levels' prediction heads beside each other; level 2 (default): also the
+# decoder's independent chains (k / v projections, box / size heads off the critical path, hoisted key-value and value projections)
+BRANCH_LEVEL = 0 if not _BRANCHES else int(os.environ.get("MDB_BRANCH_LEVEL", "2"))
 
 
 class Branch:
@@ -61,10 +64,10 @@ class Branch:
     consumer side).  Autograd replays every node's backward on the stream its forward ran on, so the backward of the branch
     overlaps too; inside a CUDA-graph capture this is the ordinary fork / join.  `MDB_NO_BRANCH_STREAMS=1` makes it a no-op."""
 
-    def __init__(self, index):
+    def __init__(self, index, level=1):
         self.main = torch.cuda.current_stream()
         self.side = None
-        if _BRANCHES:
+        if BRANCH_LEVEL >= level:
             key = (torch.cuda.current_device(), index)
             self.side = _BRANCH_STREAMS.get(key)
             if self.side is None:

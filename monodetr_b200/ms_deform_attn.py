@@ -46,15 +46,21 @@ class MSDeformAttn(nn.Module):
         xavier_uniform_(self.output_proj.weight.data)
         constant_(self.output_proj.bias.data, 0.)
 
-    def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
-                input_padding_mask=None):
-        """Same arguments as the reference (:122-134); returns (N, Len_q, C)."""
-        N, Len_q, _ = query.shape
+    def project_value(self, input_flatten, input_padding_mask=None):
+        """value_proj + padding fill (:136-139): depends on the memory only, so a caller may run it ahead of the query path."""
         N, Len_in, _ = input_flatten.shape
         value = Fn.linear(input_flatten, self.value_proj.weight, self.value_proj.bias)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], float(0))
-        value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
+        return value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
+
+    def forward(self, query, reference_points, input_flatten, input_spatial_shapes, input_level_start_index,
+                input_padding_mask=None, value=None):
+        """Same arguments as the reference (:122-134) (+ `value`: the result of `project_value`, if already computed);
+        returns (N, Len_q, C)."""
+        N, Len_q, _ = query.shape
+        if value is None:
+            value = self.project_value(input_flatten, input_padding_mask)
         sampling_offsets = Fn.linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias)
         attention_logits = Fn.linear(query, self.attention_weights.weight, self.attention_weights.bias)
         if self.freeze_sampling_locations:
