@@ -115,7 +115,26 @@ class MonoDETR(nn.Module):
 
     def _forward(self, images, calibs, targets, img_sizes, dn_args=None):
         features, pos = self.backbone(images)                                      # NHWC maps, (HW, C) tables
-        srcs = [self.input_proj[l](feat) for l, feat in enumerate(features)]
+        # The neck's projections are independent per level (the three coarse ones are tiny): the finest level stays on this
+        # stream, the others run beside it.
+        srcs, neck = [None] * len(features), []
+        for l in range(len(features) - 1, 0, -1):
+            br = Fn.Branch(15 + l, level=2)
+            with br:
+                srcs[l] = self.input_proj[l](features[l])
+            neck.append((br, l))
+        extra = None
+        if self.num_feature_levels == len(features) + 1:
+            extra = Fn.Branch(15, level=2)
+            with extra:
+                src_extra = self.input_proj[len(features)](features[-1])
+        srcs[0] = self.input_proj[0](features[0])
+        for br, l in neck:
+            br.join(srcs[l])
+        if extra is not None:
+            extra.join(src_extra)
+            srcs.append(src_extra)
+            pos.append(self.backbone[1](src_extra))
         for l in range(len(srcs), self.num_feature_levels):
             src = self.input_proj[l](features[-1] if l == len(features) else srcs[-1])
             srcs.append(src)
