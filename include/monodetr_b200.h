@@ -32,6 +32,18 @@ int mdb_abi_version(void);
 /* Human-readable name of the last error code returned on this thread ("ok" if 0). HOST string. */
 const char* mdb_error_string(int code);
 
+/* Reproducible accumulation (process-wide; default 0).  The reference scatters the MSDeformAttn value gradient with atomicAdd
+ * (ms_deform_im2col_cuda.cuh:125-152) and so does the default path here (vector reductions), as does the split-K weight gradient
+ * of the tensor-core family: results then differ in the last bits from run to run.  With 1:
+ *   - mdb_msda_backward_f32 / _f64 accumulate grad_value in a FIXED order (one thread owns each element and adds its
+ *     contributions in (query, point, corner) order with plain read-modify-writes; grad_loc / grad_attn never use atomics),
+ *   - mdb_msda_fused_backward_f32 returns MDB_EUNSUPPORTED (callers take mdb_msda_prep_* + mdb_msda_backward_*),
+ *   - mdb_conv2d_wgrad_* run without split-K (exactly one accumulation per output element),
+ * so that two runs on the same inputs give the same bits.  A test / debugging mode: the ordered scatter is ~20x slower.
+ * (Per-channel parameter gradients of the norm layers and the GroupNorm statistics still combine CTA partials atomically.) */
+int mdb_set_deterministic(int on);
+int mdb_get_deterministic(void);
+
 /* ---- Multi-scale deformable attention (MSDeformAttn core) -----------------------------------
  * value          (B, S, M, D)          contiguous
  * spatial_shapes (L, 2) int64 (H_l, W_l), device        [ms_deform_attn_cuda.cu:28-38 asserts the same]

@@ -10,4 +10,20 @@ def build_monodetr(cfg, criterion_builder=None):
     return build(cfg, criterion_builder)
 
 
-__all__ = ["build_monodetr"]
+def set_deterministic(on=True):
+    """Reproducible accumulation for the two large scatter sites (`mdb_set_deterministic`, include/monodetr_b200.h): the
+    MSDeformAttn value gradient is accumulated in a fixed order (the reference's kernel and the default path here scatter
+    with atomics, ms_deform_im2col_cuda.cuh:125-152) and weight gradients run without split-K.  A test / debugging mode
+    (much slower); set it before the forward pass.  Returns the previous setting."""
+    from . import _lib
+    prev = bool(_lib.lib().mdb_get_deterministic())
+    _lib.check(_lib.lib().mdb_set_deterministic(1 if on else 0), "set_deterministic")
+    return prev
+
+
+def is_deterministic():
+    from . import _lib
+    return bool(_lib.lib().mdb_get_deterministic())
+
+
+__all__ = ["build_monodetr", "set_deterministic", "is_deterministic"]

@@ -24,6 +24,8 @@ SIGNATURES = {
     "mdb_msda_fused_backward_f32": [_PTR] * 7 + [c_int] * 8 + [_PTR] * 4,
     "mdb_msda_prep_forward_f32": [_PTR] * 4 + [c_int] * 6 + [_PTR] * 3,
     "mdb_msda_prep_backward_f32": [_PTR] * 5 + [c_int] * 6 + [_PTR] * 3,
+    "mdb_set_deterministic": [c_int],
+    "mdb_get_deterministic": [],
     "mdb_set_precision": [c_int],
     "mdb_get_precision": [],
     "mdb_conv2d_forward_f32": [_PTR] * 5 + [c_int] * 10 + [_PTR],

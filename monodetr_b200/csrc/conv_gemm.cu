@@ -1338,7 +1338,7 @@ int mdb_conv2d_wgrad_bias_f32(const float* dy, const float* x, const float* rows
     if (big > total_red / 24) big = total_red / 24;
     if (small > total_red / 8) small = total_red / 8;
     int splits = big > small ? big : small;
-    if (splits < 1) splits = 1;
+    if (splits < 1 || mdb_get_deterministic()) splits = 1;      // reproducible mode: exactly one accumulation per output element
     p.red_per_split = (total_red + splits - 1) / splits;
     splits = (total_red + p.red_per_split - 1) / p.red_per_split;
     p.w_sy = p.w_sx = stride;

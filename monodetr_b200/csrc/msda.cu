@@ -531,7 +531,7 @@ __device__ __forceinline__ T warp_sum(T v) {
     return v;
 }
 
-template <typename T>
+template <typename T, bool SCATTER = true>
 __global__ void __launch_bounds__(kThreads)
 msda_bwd_generic_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
                         const int64_t* __restrict__ lsi, const T* __restrict__ loc,
@@ -565,10 +565,10 @@ msda_bwd_generic_kernel(const T* __restrict__ value, const int64_t* __restrict__
                         const T g = grad_out[(size_t)unit * D + c];
                         const T tg = g * a;
                         T v1 = 0, v2 = 0, v3 = 0, v4 = 0;
-                        if (top && lef) { v1 = value[o00 + c]; atomicAdd(grad_value + o00 + c, (hy * hx) * tg); }
-                        if (top && rig) { v2 = value[o01 + c]; atomicAdd(grad_value + o01 + c, (hy * lx) * tg); }
-                        if (bot && lef) { v3 = value[o10 + c]; atomicAdd(grad_value + o10 + c, (ly * hx) * tg); }
-                        if (bot && rig) { v4 = value[o11 + c]; atomicAdd(grad_value + o11 + c, (ly * lx) * tg); }
+                        if (top && lef) { v1 = value[o00 + c]; if constexpr (SCATTER) atomicAdd(grad_value + o00 + c, (hy * hx) * tg); }
+                        if (top && rig) { v2 = value[o01 + c]; if constexpr (SCATTER) atomicAdd(grad_value + o01 + c, (hy * lx) * tg); }
+                        if (bot && lef) { v3 = value[o10 + c]; if constexpr (SCATTER) atomicAdd(grad_value + o10 + c, (ly * hx) * tg); }
+                        if (bot && rig) { v4 = value[o11 + c]; if constexpr (SCATTER) atomicAdd(grad_value + o11 + c, (ly * lx) * tg); }
                         ga += g * ((hy * hx) * v1 + (hy * lx) * v2 + (ly * hx) * v3 + (ly * lx) * v4);
                         gx += tg * (hy * (v2 - v1) + ly * (v4 - v3));
                         gy += tg * (hx * (v3 - v1) + lx * (v4 - v2));
@@ -582,6 +582,48 @@ msda_bwd_generic_kernel(const T* __restrict__ value, const int64_t* __restrict__
                     grad_loc[2 * pi] = (T)W * gx;
                     grad_loc[2 * pi + 1] = (T)H * gy;
                 }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reproducible value gradient (mdb_set_deterministic(1)): CTA (b, m, l) owns grad_value[b, level l, head m, :]; thread c owns
+// channels c, c + blockDim, ... and adds the contributions of every (query, point, corner) IN THAT ORDER with plain
+// read-modify-writes -- no element is ever touched by two threads, so the result is bit-identical from run to run (and
+// independent of the grid).  Same arithmetic as the scatter: contribution = (bilinear weight) * (grad_out * attention weight).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+msda_bwd_value_ordered_kernel(const int64_t* __restrict__ shapes, const int64_t* __restrict__ lsi, const T* __restrict__ loc,
+                              const T* __restrict__ attn, const T* __restrict__ grad_out, int S, int M, int D, int L, int Lq,
+                              int P, T* grad_value) {
+    const int l = (int)(blockIdx.x % L);
+    const int m = (int)((blockIdx.x / L) % M);
+    const long long b = blockIdx.x / ((long long)L * M);
+    const int H = (int)shapes[2 * l], W = (int)shapes[2 * l + 1];
+    const size_t pix = (size_t)M * D;
+    const size_t lbase = ((size_t)b * S + (size_t)lsi[l]) * pix + (size_t)m * D;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        for (int q = 0; q < Lq; ++q) {
+            const size_t unit = ((size_t)b * Lq + q) * M + m;
+            const T g = grad_out[unit * D + c];
+            for (int p = 0; p < P; ++p) {
+                const size_t pi = (unit * L + l) * P + p;
+                const T x = fma_t(loc[2 * pi], (T)W, (T)-0.5);
+                const T y = fma_t(loc[2 * pi + 1], (T)H, (T)-0.5);
+                if (!(y > (T)-1 && x > (T)-1 && y < (T)H && x < (T)W)) continue;
+                const T tg = g * attn[pi];
+                const T xf = floor_t(x), yf = floor_t(y);
+                const int x0 = (int)xf, y0 = (int)yf;
+                const T lx = x - xf, ly = y - yf, hx = (T)1 - lx, hy = (T)1 - ly;
+                const bool top = y0 >= 0, bot = y0 + 1 <= H - 1, lef = x0 >= 0, rig = x0 + 1 <= W - 1;
+                const long long o00 = (long long)lbase + ((long long)y0 * W + x0) * (long long)pix + c;
+                const long long o01 = o00 + (long long)pix, o10 = o00 + (long long)W * pix, o11 = o10 + pix;
+                if (top && lef) grad_value[o00] += (hy * hx) * tg;
+                if (top && rig) grad_value[o01] += (hy * lx) * tg;
+                if (bot && lef) grad_value[o10] += (ly * hx) * tg;
+                if (bot && rig) grad_value[o11] += (ly * lx) * tg;
             }
         }
     }
@@ -674,6 +716,18 @@ int backward_impl(const T* value, const int64_t* shapes, const int64_t* lsi, con
         return (int)cudaMemsetAsync(grad_attn, 0, sizeof(T) * (size_t)n_units * L * P, stream);
     }
     if (!grad_out) return MDB_EINVAL;
+    if (mdb_get_deterministic()) {
+        // grad_loc / grad_attn by the generic kernel (warp reductions, no atomics) with its scatter compiled out, then the
+        // value gradient in a fixed accumulation order
+        const int grid = grid_for(n_units, 8);
+        msda_bwd_generic_kernel<T, false><<<grid, kThreads, 0, stream>>>(value, shapes, lsi, loc, attn, grad_out, S, M, D, L, Lq, P, n_units, grad_value, grad_loc, grad_attn);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+        int threads = (D + 31) / 32 * 32;
+        if (threads > kThreads) threads = kThreads;
+        msda_bwd_value_ordered_kernel<T><<<(unsigned)((long long)B * M * L), threads, 0, stream>>>(shapes, lsi, loc, attn, grad_out, S, M, D, L, Lq, P, grad_value);
+        return (int)cudaGetLastError();
+    }
     if constexpr (sizeof(T) == 4) {
         const bool fast = (P == 4) && (L == 4) && (D == 16 || D == 32 || D == 64) && aligned16(value) &&
                           aligned16(loc) && aligned16(attn) && aligned16(grad_out) && aligned16(grad_value);
@@ -743,6 +797,7 @@ int mdb_msda_fused_backward_f32(const float* value, const int64_t* spatial_shape
                                 const float* logits, const float* ref, const float* grad_out, int B, int S, int M, int D, int L, int Lq,
                                 int P, int ref_dim, float* grad_value, float* grad_offsets, float* grad_logits, void* stream_) {
     if (D != 32 || L != 4 || P != 4 || (ref_dim != 2 && ref_dim != 6)) return MDB_EUNSUPPORTED;
+    if (mdb_get_deterministic()) return MDB_EUNSUPPORTED;      // ordered accumulation: mdb_msda_prep_* + mdb_msda_backward_*
     int rc = check_common(value, spatial_shapes, level_start, offsets, logits, B, S, M, D, L, Lq, P);
     if (rc) return rc;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -429,7 +429,8 @@ class _MsdaFused(Function):
 
 def msda_fused_applicable(value, ref, n_levels, n_points):
     return (value.dtype == torch.float32 and value.shape[-1] == 32 and n_levels == 4 and n_points == 4 and not ref.requires_grad
-            and ref.shape[-1] in (2, 6) and not os.environ.get("MDB_MSDA_UNFUSED"))
+            and ref.shape[-1] in (2, 6) and not os.environ.get("MDB_MSDA_UNFUSED")
+            and not _lib.lib().mdb_get_deterministic())      # reproducible mode: ordered scatter of the two-step path
 
 
 def msda_fused(value, spatial_shapes, level_start_index, off, logits, ref):

@@ -209,3 +209,71 @@ def test_fused_preprocessing_matches_the_two_step_path(Lq, rd, B):
     _close(go, ro, 1e-4, 1e-5, "grad_offsets")
     _close(gl, rl, 1e-4, 1e-5, "grad_logits")
     assert not Fn.msda_fused_applicable(ins[0], ref.clone().requires_grad_(), 4, 4)      # boxes that need a gradient: two-step path
+
+
+@pytest.fixture
+def deterministic_mode():
+    import monodetr_b200
+    prev = monodetr_b200.set_deterministic(True)
+    try:
+        yield
+    finally:
+        monodetr_b200.set_deterministic(prev)
+
+
+@pytest.mark.parametrize("cfg", [
+    (FULL_SHAPES, 2, 8, 32, 1100, 4, torch.float32),                            # the model's configuration (fast-path shape)
+    ([(9, 11), (4, 5), (2, 2), (1, 1)], 2, 6, 16, 40, 4, torch.float32),
+    ([(6, 4), (3, 2)], 1, 2, 71, 6, 2, torch.float64),                          # generic shapes: ragged D, fp64
+])
+def test_deterministic_backward_is_bit_reproducible_and_matches_the_oracle(cfg, deterministic_mode):
+    """mdb_set_deterministic(1): the value gradient is accumulated in a fixed order (the default path and the reference's
+    kernel, ms_deform_im2col_cuda.cuh:125-152, scatter with atomics): two runs give the same bits, the values are the oracle's,
+    and they agree with the default (atomic) path to rounding.  Points are concentrated so that rows really collide."""
+    from monodetr_b200.msda import ms_deform_attn_backward
+    import monodetr_b200
+    shapes, N, M, D, Lq, P, dtype = cfg
+    shapes_t, lsi, value, loc, attn, grad_out = _make(11 + Lq, shapes, N, M, D, Lq, P, dtype, 0.3, 0.7)
+    dv = [t.cuda() for t in (value, shapes_t, lsi, loc, attn, grad_out)]
+    runs = [ms_deform_attn_backward(*dv, 64) for _ in range(2)]
+    torch.cuda.synchronize()
+    for a, b in zip(*runs):
+        assert torch.equal(a, b)
+    rtol, atol = _tol(dtype)
+    npv = [t.numpy() for t in (value, shapes_t, lsi, loc, attn)]
+    for got, want, name in zip(runs[0], oracle_msda.msda_backward(*npv, grad_out.numpy()), ("grad_value", "grad_loc", "grad_attn")):
+        _close(got, want, 2 * rtol, 2 * atol, name)
+    monodetr_b200.set_deterministic(False)
+    try:
+        default = ms_deform_attn_backward(*dv, 64)
+    finally:
+        monodetr_b200.set_deterministic(True)
+    for got, want, name in zip(runs[0], default, ("grad_value", "grad_loc", "grad_attn")):
+        _close(got, want, 2 * rtol, 2 * atol, name + " vs the atomic path")
+
+
+def test_deterministic_module_path_takes_the_ordered_scatter(deterministic_mode):
+    """In the reproducible mode the MSDeformAttn module leaves the fused kernels (whose backward scatters with vector
+    reductions) for the two-step path, and a whole module forward + backward is bit-identical from run to run."""
+    from monodetr_b200 import functional as Fn
+    from monodetr_b200.ms_deform_attn import MSDeformAttn
+    torch.manual_seed(3)
+    mod = MSDeformAttn(256, 4, 8, 4).cuda()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    shapes = [(12, 40), (6, 20), (3, 10), (2, 5)]
+    shapes_t = torch.as_tensor(shapes, dtype=torch.long, device="cuda")
+    lsi = torch.cat((shapes_t.new_zeros((1,)), shapes_t.prod(1).cumsum(0)[:-1]))
+    S = int(shapes_t.prod(1).sum())
+    src = torch.randn(2, S, 256, device="cuda", generator=g)
+    query = torch.randn(2, 300, 256, device="cuda", generator=g)
+    ref = torch.rand(2, 300, 4, 2, device="cuda", generator=g) * 0.2 + 0.4
+    dout = torch.randn(2, 300, 256, device="cuda", generator=g)
+    assert not Fn.msda_fused_applicable(src.view(2, S, 8, 32), ref, 4, 4)
+    grads = []
+    for _ in range(2):
+        s, q = src.clone().requires_grad_(), query.clone().requires_grad_()
+        out = mod(q, ref, s, shapes_t, lsi)
+        params = [mod.value_proj.weight, mod.sampling_offsets.weight, mod.attention_weights.weight, mod.output_proj.weight]
+        grads.append((out.detach(),) + torch.autograd.grad(out, [s, q] + params, dout))
+    for a, b in zip(*grads):
+        assert torch.equal(a, b)
