@@ -357,8 +357,9 @@ def main():
         line = run_msda_b200(args, rank, local_rank, ws)
     else:
         from monodetr_b200 import bench_model
-        line = bench_model.run(args, rank, local_rank, ws, infer=(args.workload == "infer"))
-        if line is not None and ws == 1 and args.workload == "model":
+        quick = bool(os.environ.get("MDB_BENCH_QUICK"))      # A/B runs: the timed step and e2e only (no probes, batch-16 point, CPU arm, extras)
+        line = bench_model.run(args, rank, local_rank, ws, infer=(args.workload == "infer"), extras=not quick)
+        if line is not None and ws == 1 and args.workload == "model" and not quick:
             if not args.batch and not os.environ.get("MDB_BENCH_NO_B16"):
                 # the N > 1 runs use batch 16 per GPU (BASELINE configs[3]): the like-for-like single-GPU point for scaling
                 import gc

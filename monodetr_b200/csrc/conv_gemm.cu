@@ -214,6 +214,14 @@ tc_conv_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch (launch_tc): everything above -- barrier init, tensor-map prefetch, TMEM allocation --
+    // touches no global data and may run while the previous kernel of the stream is still finishing; every thread waits here
+    // (before any role reads or writes global memory, and before any thread can exit, so that completion of this grid implies
+    // completion of its predecessors) until that kernel has completed and its writes are visible.  A no-op for a normal launch.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // ... and let the NEXT kernel of the stream (if it was launched as a programmatic dependent) start its own prologue now:
+    // it waits at the same point for this grid to complete.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp == 0) {
         // ================================ TMA producer =============================================
@@ -899,6 +907,25 @@ int launch_tc(const CUtensorMap& a, const CUtensorMap& b, TcParams p, dim3 grid,
     int ctas = num_sms_tc() * resident;
     if (ctas > p.total_tiles) ctas = p.total_tiles;
     if (ctas < 1) return 0;
+    // Launch as a PROGRAMMATIC DEPENDENT of the previous kernel in the stream (CUDA >= 11.8, graph capture >= 12.3; MDB_NO_PDL=1: plain launch): the
+    // grid may be scheduled while that kernel drains, runs its prologue and then blocks in griddepcontrol.wait until the
+    // predecessor has completed (see the kernel) -- the launch latency and the prologue of the ~470 GEMM launches of a training
+    // step leave the critical path.  Other stream dependencies (events, memsets, copies) stay full dependencies.
+    static const bool pdl = getenv("MDB_NO_PDL") == nullptr;
+    if (pdl) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)ctas, 1, 1);
+        cfg.blockDim = dim3((unsigned)threads, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return (int)cudaLaunchKernelEx(&cfg, kern, a, b, o ? *o : a, r ? *r : a, m ? *m : a, p);
+    }
     kern<<<ctas, threads, smem, stream>>>(a, b, o ? *o : a, r ? *r : a, m ? *m : a, p);
     return (int)cudaGetLastError();
 }

@@ -56,6 +56,9 @@ class VisualEncoderLayer(nn.Module):
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, padding_mask=None):
         sb = self.site_base
+        if (self.dropout1.p == self.dropout2.p == self.dropout3.p and pos is not None
+                and Fn.encoder_layer_fusable(self, src, reference_points, padding_mask)):
+            return Fn.encoder_layer(self, src, pos, reference_points, spatial_shapes, level_start_index)   # one autograd node
         src2 = self.self_attn(src + pos, reference_points, src, spatial_shapes, level_start_index, padding_mask)
         src = Fn.add_layernorm(src, src2, self.norm1.weight, self.norm1.bias, self.norm1.eps, self.dropout1.p, self.training, sb)
         h = Fn.linear(src, self.linear1.weight, self.linear1.bias, relu=True)

@@ -59,6 +59,10 @@ _BRANCHES = not os.environ.get("MDB_NO_BRANCH_STREAMS")
 BRANCH_LEVEL = 0 if not _BRANCHES else int(os.environ.get("MDB_BRANCH_LEVEL", "2"))
 
 
+# weight re-layout / (hi, lo) splitting of a forward pass on a branch stream beside the ResNet stem (MDB_NO_PACK_OVERLAP=1: in line)
+PACK_OVERLAP = not os.environ.get("MDB_NO_PACK_OVERLAP")
+
+
 class Branch:
     """Run an independent part of the forward graph on its own stream (`with Branch(i): ...`, then `.join(*outputs)` on the
     consumer side).  Autograd replays every node's backward on the stream its forward ran on, so the backward of the branch
@@ -389,6 +393,35 @@ def msda_prep(off, logits, ref, spatial_shapes, M, L, P):
     return _MsdaPrep.apply(off, logits, ref, spatial_shapes, M, L, P)
 
 
+def msda_fused_forward_raw(value, shapes, lsi, off, logits, refc):
+    """mdb_msda_fused_forward_f32 on contiguous tensors (value (B,S,M,32), raw offsets / logits, constant reference points)."""
+    B, S, M, D = value.shape
+    Lq, rd = off.shape[1], refc.shape[-1]
+    out = torch.empty((B, Lq, M * D), dtype=torch.float32, device=value.device)
+    from . import msda as _m
+    if _m.PROBE is not None:        # bench.py: CUDA events tight around the launch (nothing else between them)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.check(_lib.lib().mdb_msda_fused_forward_f32(_p(value), _p(shapes), _p(lsi), _p(off), _p(logits), _p(refc), B, S, M, D, 4, Lq, 4, rd,
+                                                     _p(out), _s()), "msda_fused_forward")
+    if _m.PROBE is not None:
+        e1.record()
+        _m.PROBE.append((e0, e1, B, Lq))
+    _lib.count(1)
+    return out
+
+
+def msda_fused_backward_raw(value, shapes, lsi, off, logits, refc, dout):
+    B, S, M, D = value.shape
+    Lq, rd = off.shape[1], refc.shape[-1]
+    dout = dout.contiguous()
+    gv, goff, glog = torch.empty_like(value), torch.empty_like(off), torch.empty_like(logits)
+    _lib.check(_lib.lib().mdb_msda_fused_backward_f32(_p(value), _p(shapes), _p(lsi), _p(off), _p(logits), _p(refc), _p(dout), B, S, M, D, 4, Lq,
+                                                      4, rd, _p(gv), _p(goff), _p(glog), _s()), "msda_fused_backward")
+    _lib.count(1)
+    return gv, goff, glog
+
+
 class _MsdaFused(Function):
     """value (B,S,M,32), raw offsets (B,Lq,M*4*4*2), raw logits (B,Lq,M*16), constant reference points (B,Lq,4,rd) -> (B,Lq,M*32):
     softmax / sampling-location pre-processing inside the sampling kernels (forward and backward)."""
@@ -397,19 +430,7 @@ class _MsdaFused(Function):
     def forward(ctx, value, shapes, lsi, off, logits, ref):
         value, off, logits = value.contiguous(), off.contiguous(), logits.contiguous()
         refc = ref.detach().contiguous()
-        B, S, M, D = value.shape
-        Lq, rd = off.shape[1], refc.shape[-1]
-        out = torch.empty((B, Lq, M * D), dtype=torch.float32, device=value.device)
-        from . import msda as _m
-        if _m.PROBE is not None:        # bench.py: CUDA events tight around the launch (nothing else between them)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        _lib.check(_lib.lib().mdb_msda_fused_forward_f32(_p(value), _p(shapes), _p(lsi), _p(off), _p(logits), _p(refc), B, S, M, D, 4, Lq, 4, rd,
-                                                         _p(out), _s()), "msda_fused_forward")
-        if _m.PROBE is not None:
-            e1.record()
-            _m.PROBE.append((e0, e1, B, Lq))
-        _lib.count(1)
+        out = msda_fused_forward_raw(value, shapes, lsi, off, logits, refc)
         ctx.save_for_backward(value, shapes, lsi, off, logits, refc)
         return out
 
@@ -417,13 +438,7 @@ class _MsdaFused(Function):
     @once_differentiable
     def backward(ctx, dout):
         value, shapes, lsi, off, logits, refc = ctx.saved_tensors
-        B, S, M, D = value.shape
-        Lq, rd = off.shape[1], refc.shape[-1]
-        dout = dout.contiguous()
-        gv, goff, glog = torch.empty_like(value), torch.empty_like(off), torch.empty_like(logits)
-        _lib.check(_lib.lib().mdb_msda_fused_backward_f32(_p(value), _p(shapes), _p(lsi), _p(off), _p(logits), _p(refc), _p(dout), B, S, M, D, 4, Lq,
-                                                          4, rd, _p(gv), _p(goff), _p(glog), _s()), "msda_fused_backward")
-        _lib.count(1)
+        gv, goff, glog = msda_fused_backward_raw(value, shapes, lsi, off, logits, refc, dout)
         return gv, None, None, goff, glog, None
 
 
@@ -435,6 +450,112 @@ def msda_fused_applicable(value, ref, n_levels, n_points):
 
 def msda_fused(value, spatial_shapes, level_start_index, off, logits, ref):
     return _MsdaFused.apply(value, spatial_shapes, level_start_index, off, logits, ref)
+
+
+# ---- one encoder layer as ONE autograd node ---------------------------------------------------------------------------
+ENC_FUSED = not os.environ.get("MDB_NO_ENC_FUSED")
+
+
+class _EncoderLayer(Function):
+    """VisualEncoderLayer.forward (depthaware_transformer.py:315-354: deformable self-attention -> dropout / residual / LayerNorm ->
+    FFN -> dropout / residual / LayerNorm) as ONE autograd node over the same kernels the separate nodes launch, so that the
+    backward can hand every fan-in sum to a GEMM epilogue instead of autograd's stand-alone additions over (B, S, C) tensors:
+      * d src1 = dgrad(linear1) + (LayerNorm-2 residual gradient)          -> residual operand of the dgrad epilogue
+      * d query = dgrad(sampling_offsets) + dgrad(attention_weights)       -> residual operand
+      * d src  = dgrad(value_proj) + (LayerNorm-1 residual gradient) [+ d query: the one addition left]
+      * the ReLU mask of linear1 rides in linear2's dgrad epilogue (was a separate pass)
+    Per layer 4 of 5 additions and the ReLU pass over 84 MB tensors disappear (B = 8, 1280 x 384).  Forward values are
+    bit-identical to the separate nodes (same kernels, same order); gradients differ by the association of those sums."""
+
+    @staticmethod
+    def forward(ctx, src, pos, ref, shapes, lsi, n_heads, eps1, eps2, p, training, site,
+                Wv, bv, Wo, bo, Wa, ba, Wu, bu, g1, be1, W1, b1, W2, b2, g2, be2):
+        B, S, C = src.shape
+        M = B * S
+        src = src.contiguous()
+        q = src + pos
+        x2, q2 = src.view(M, C), q.view(M, C)
+        sv, so, sa, su, s1, s2 = (tc.lookup_split(w) for w in (Wv, Wo, Wa, Wu, W1, W2))
+        value = tc.linear_forward(x2, sv, bv)
+        off = tc.linear_forward(q2, so, bo)
+        logits = tc.linear_forward(q2, sa, ba)
+        refc = ref.detach().contiguous()
+        o = msda_fused_forward_raw(value.view(B, S, n_heads, C // n_heads), shapes, lsi, off.view(B, S, -1), logits.view(B, S, -1), refc)
+        o2 = o.view(M, C)
+        a = tc.linear_forward(o2, su, bu)
+        drop = float(p) if training else 0.0
+        seed = K.seed_tensor(src.device) if drop > 0 else None
+        src1, mean1, rstd1 = K.add_layernorm_forward(x2, a, g1, be1, eps1, drop, site, seed)
+        h = tc.linear_forward(src1, s1, b1, relu=True)
+        hd = dropout_raw(h, drop, site + 1, seed) if drop > 0 else h
+        f = tc.linear_forward(hd, s2, b2)
+        out, mean2, rstd2 = K.add_layernorm_forward(src1, f, g2, be2, eps2, drop, site + 2, seed)
+        ctx.save_for_backward(x2, q2, value, off, logits, refc, o2, a, src1, mean1, rstd1, h, hd if drop > 0 else None, f,
+                              mean2, rstd2, shapes, lsi, g1, g2)
+        ctx.splits = (sv, so, sa, su, s1, s2)
+        ctx.meta = (B, S, C, n_heads, drop, site, pos.shape)
+        ctx.seed = seed
+        return out.view(B, S, C)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        (x2, q2, value, off, logits, refc, o2, a, src1, mean1, rstd1, h, hd, f, mean2, rstd2, shapes, lsi, g1, g2) = ctx.saved_tensors
+        sv, so, sa, su, s1, s2 = ctx.splits
+        B, S, C, n_heads, drop, site, pos_shape = ctx.meta
+        seed = ctx.seed
+        M = B * S
+        if hd is None:
+            hd = h
+        # ---- LayerNorm 2, FFN ------------------------------------------------------------------------------------------------
+        d_src1_res, d_f, dg2, dbe2 = K.add_layernorm_backward(dout.reshape(M, C), src1, f, g2, mean2, rstd2, drop, site + 2, seed)
+        dW2, db2 = tc.linear_wgrad(d_f, hd, with_bias_grad=True)
+        d_h = tc.linear_dgrad(d_f, s2, relu_mask=h)                        # ReLU mask in the epilogue (commutes with the dropout scaling)
+        if drop > 0:
+            d_h = dropout_raw(d_h, drop, site + 1, seed)
+        dW1, db1 = tc.linear_wgrad(d_h, src1, with_bias_grad=True)
+        d_src1 = tc.linear_dgrad(d_h, s1, residual=d_src1_res)             # + the residual branch of LayerNorm 2
+        # ---- LayerNorm 1, output projection, deformable attention ----------------------------------------------------------
+        d_x_res, d_a, dg1, dbe1 = K.add_layernorm_backward(d_src1, x2, a, g1, mean1, rstd1, drop, site, seed)
+        dWu, dbu = tc.linear_wgrad(d_a, o2, with_bias_grad=True)
+        d_o = tc.linear_dgrad(d_a, su)
+        gv, goff, glog = msda_fused_backward_raw(value.view(B, S, n_heads, C // n_heads), shapes, lsi, off.view(B, S, -1),
+                                                 logits.view(B, S, -1), refc, d_o.view(B, S, C))
+        gv2, goff2, glog2 = gv.view(M, C), goff.view(M, -1), glog.view(M, -1)
+        dWo, dbo = tc.linear_wgrad(goff2, q2, with_bias_grad=True)
+        dWa, dba = tc.linear_wgrad(glog2, q2, with_bias_grad=True)
+        dWv, dbv = tc.linear_wgrad(gv2, x2, with_bias_grad=True)
+        d_q = tc.linear_dgrad(goff2, so)
+        d_q = tc.linear_dgrad(glog2, sa, residual=d_q)                     # d query = both projections' data gradients
+        d_pos = d_q.view(B, S, C).sum_to_size(pos_shape) if ctx.needs_input_grad[1] else None
+        d_src = tc.linear_dgrad(gv2, sv, residual=d_x_res)                 # + the residual branch of LayerNorm 1
+        d_src.add_(d_q)                                                     # + the query path (query = src + pos)
+        return (d_src.view(B, S, C), d_pos, None, None, None, None, None, None, None, None, None,
+                dWv, dbv, dWo, dbo, dWa, dba, dWu, dbu, dg1, dbe1, dW1, db1, dW2, db2, dg2, dbe2)
+
+
+def encoder_layer_fusable(layer, src, reference_points, padding_mask):
+    """The fused node covers the configuration the model runs (configs/monodetr.yaml): BF16x3 arithmetic, D = 32 x 4 levels x 4
+    points with constant reference points, no padding mask; anything else takes the separate nodes."""
+    att = layer.self_attn
+    dims_ok = all(w.shape[0] % 4 == 0 and w.shape[1] % 4 == 0 for w in (att.sampling_offsets.weight, att.attention_weights.weight,
+                                                                         layer.linear1.weight, layer.linear2.weight))
+    return (ENC_FUSED and src.is_cuda and src.dtype == torch.float32 and padding_mask is None and tc.get_precision() == "bf16x3"
+            and not getattr(att, "freeze_sampling_locations", False) and dims_ok and src.dim() == 3
+            and src.shape[-1] // att.n_heads == 32 and src.shape[-1] % att.n_heads == 0
+            and msda_fused_applicable(src.reshape(src.shape[0], src.shape[1], att.n_heads, -1), reference_points, att.n_levels, att.n_points)
+            and all(m.bias is not None for m in (att.value_proj, att.sampling_offsets, att.attention_weights, att.output_proj,
+                                                 layer.linear1, layer.linear2)))
+
+
+def encoder_layer(layer, src, pos, reference_points, spatial_shapes, level_start_index):
+    att = layer.self_attn
+    return _EncoderLayer.apply(src, pos, reference_points, spatial_shapes, level_start_index, att.n_heads, layer.norm1.eps,
+                               layer.norm2.eps, layer.dropout1.p, layer.training, layer.site_base,
+                               att.value_proj.weight, att.value_proj.bias, att.sampling_offsets.weight, att.sampling_offsets.bias,
+                               att.attention_weights.weight, att.attention_weights.bias, att.output_proj.weight, att.output_proj.bias,
+                               layer.norm1.weight, layer.norm1.bias, layer.linear1.weight, layer.linear1.bias,
+                               layer.linear2.weight, layer.linear2.bias, layer.norm2.weight, layer.norm2.bias)
 
 
 class _DepthSample(Function):
