@@ -105,16 +105,6 @@ class _ResNetFn(Function):
         shifts = tensors[2 * nconv:3 * nconv]
         B, _, H, W = images.shape
         dev = images.device
-        # all bottleneck weights re-laid-out to [tap][O][I] with the BN scale folded in by ONE launch per 64 tensors (52 tensors).
-        # Nothing before layer1's first convolution reads them, so the (memory-bound) re-layout runs on a branch stream beside the
-        # (FMA-bound) stem and is joined after the max-pool.
-        from .functional import Branch, PACK_OVERLAP
-        pack_branch = Branch(30, level=1 if PACK_OVERLAP else 99)
-        with pack_branch:
-            if tc.get_precision() == "bf16x3":  # (hi, lo) bf16 operands for fprop and dgrad, BN scale folded before the split
-                all_wp = [None] + tc.split_weights([w.detach() for w in weights[1:nconv]], list(scales[1:nconv]))
-            else:
-                all_wp = [None] + tc.pack_weights_multi(list(weights[1:nconv]), list(scales[1:nconv]))
         # ---- stem (frozen) --------------------------------------------------------------------------------
         H1, W1 = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
         y = torch.empty((B, H1, W1, 64), dtype=torch.float32, device=dev)
@@ -127,8 +117,13 @@ class _ResNetFn(Function):
         del y
         # ---- bottlenecks ----------------------------------------------------------------------------------
         saved, packed, feats = [], [], []
-        # (every packed weight is a view of one allocation made on the branch stream: one record_stream covers them)
-        pack_branch.join(*[t for wp_ in all_wp[1:2] for t in ((wp_.wf, wp_.wd) if isinstance(wp_, tc.SplitW) else (wp_,))])
+        # all bottleneck weights re-laid-out to [tap][O][I] with the BN scale folded in by ONE launch per 64 tensors (52 tensors).
+        # (Running this re-layout on a branch stream beside the stem was measured: 332.6 vs 332.1 img/s, within noise -- the stem
+        # fills every SM, the memory-bound re-layout only finds room in its tail; not kept.)
+        if tc.get_precision() == "bf16x3":      # (hi, lo) bf16 operands for fprop and dgrad, BN scale folded before the split
+            all_wp = [None] + tc.split_weights([w.detach() for w in weights[1:nconv]], list(scales[1:nconv]))
+        else:
+            all_wp = [None] + tc.pack_weights_multi(list(weights[1:nconv]), list(scales[1:nconv]))
         ci = 1
         for bi, (stage, stride, has_ds, trainable) in enumerate(meta["blocks"]):
             idx = [ci, ci + 1, ci + 2] + ([ci + 3] if has_ds else [])

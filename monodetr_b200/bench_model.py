@@ -302,8 +302,9 @@ def run(args, rank, local_rank, ws, infer=False, batch_override=None, extras=Tru
         ach = fwd_bytes / (enc_ms * 1e-3) / 1e9
         line["roofline"] = {"kernel": "msda_fwd_d32_kernel<fused pre-processing> (encoder call, Lq=10200, in situ)", "bound": "hbm", "achieved": ach,
                             "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                            # dram__bytes_read.sum + dram__bytes_write.sum of this launch at B=8 from the committed capture
-                            # profiles/r01_msda_fwd_d32_model.txt (239.9 MB + 72.1 MB); scaled with the batch
-                            "traffic": int(311.97e6 * B / 8),
+                            # dram__bytes_read.sum + dram__bytes_write.sum of this launch at B=8 from the committed ncu --set full
+                            # capture of the fused kernel inside the step, profiles/r02_msda_fused_fwd_step_ncu.txt
+                            # (242.4 MB + 73.2 MB); scaled with the batch
+                            "traffic": int(315.52e6 * B / 8),
                             "peak_source": pk["source"], "algorithmic_bytes": fwd_bytes, "avg_ms": enc_ms}
     return line

@@ -59,10 +59,6 @@ _BRANCHES = not os.environ.get("MDB_NO_BRANCH_STREAMS")
 BRANCH_LEVEL = 0 if not _BRANCHES else int(os.environ.get("MDB_BRANCH_LEVEL", "2"))
 
 
-# weight re-layout / (hi, lo) splitting of a forward pass on a branch stream beside the ResNet stem (MDB_NO_PACK_OVERLAP=1: in line)
-PACK_OVERLAP = not os.environ.get("MDB_NO_PACK_OVERLAP")
-
-
 class Branch:
     """Run an independent part of the forward graph on its own stream (`with Branch(i): ...`, then `.join(*outputs)` on the
     consumer side).  Autograd replays every node's backward on the stream its forward ran on, so the backward of the branch

@@ -110,25 +110,11 @@ class MonoDETR(nn.Module):
         """images (B, 3, H, W) fp32 NCHW; calibs (B, 3, 4); targets / dn_args ignored; img_sizes (B, 2) [W, H]."""
         if self.training and images.is_cuda:
             K.begin_forward(images.device)          # new dropout masks every training forward (device-side, graph-safe)
-        if not images.is_cuda:
-            with tc.prepacked([]):
-                return self._forward(images, calibs, targets, img_sizes, dn_args)
-        # The (hi, lo) split of the neck / transformer / head weights is needed after the backbone only: it runs on a branch
-        # stream beside the stem and is joined behind the backbone (before any other stream forks from this one).
-        pack_branch = Fn.Branch(31, level=1 if Fn.PACK_OVERLAP else 99)
-        with pack_branch:
-            packed = tc.prepacked(self._gemm_weights())
-            packed.__enter__()
-        try:
-            return self._forward(images, calibs, targets, img_sizes, dn_args,
-                                 after_backbone=lambda: pack_branch.join(*packed.buffers()))
-        finally:
-            packed.__exit__(None, None, None)
+        with tc.prepacked(self._gemm_weights() if images.is_cuda else []):
+            return self._forward(images, calibs, targets, img_sizes, dn_args)
 
-    def _forward(self, images, calibs, targets, img_sizes, dn_args=None, after_backbone=None):
+    def _forward(self, images, calibs, targets, img_sizes, dn_args=None):
         features, pos = self.backbone(images)                                      # NHWC maps, (HW, C) tables
-        if after_backbone is not None:
-            after_backbone()
         # The neck's projections are independent per level (the three coarse ones are tiny): the finest level stays on this
         # stream, the others run beside it.
         srcs, neck = [None] * len(features), []

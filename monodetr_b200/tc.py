@@ -121,16 +121,7 @@ class prepacked:
                 keys = list(uniq)
                 for k, sw in zip(keys, split_weights([uniq[k].detach() for k in keys])):
                     _PREPACK[k] = sw
-        self._mine = _PREPACK
         return self
-
-    def buffers(self):
-        """One tensor per allocation the split weights live in (all SplitW of one split_weights call share a flat buffer):
-        what a caller that ran __enter__ on another stream hands to record_stream."""
-        if not getattr(self, "_mine", None):
-            return []
-        sw = next(iter(self._mine.values()))
-        return [sw.wf]
 
     def __exit__(self, *a):
         global _PREPACK
