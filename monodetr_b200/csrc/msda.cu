@@ -736,6 +736,14 @@ int backward_impl(const T* value, const int64_t* shapes, const int64_t* lsi, con
             const int grid = grid_for((n_units + upw - 1) / upw, 6);
             const long long per = (kThreads / 32) * upw;
             const long long upb = ((n_units + grid - 1) / grid + per - 1) / per * per;
+            // (Round 2, third attempt at this kernel: a restructured backward organised like msda_fwd_d32_kernel -- lane c prepares points
+            // c and 8 + c, clamped unconditional corner loads and reductions without any branch, d attn / d loc from per-corner dot
+            // products through a butterfly per 8 points, 32-bit indexing: 1805 instead of ~3100 instructions per 4 units -- passed the
+            // whole parity suite and was SLOWER: 1.09 vs 0.95 ms at B=8, Lq=10200, 323.8 vs 332.0 img/s for the model step
+            // (profiles/r02_bench_msda_restructured_bwd_slower.json).  With the privatised and the merged variants that makes three
+            // ways of spending fewer instructions / fewer L2 transactions per SM that all lose: the kernel is bound by the L2's
+            // reduction throughput on the 167 M sector reductions of a call, and a denser instruction stream only queues them
+            // faster.  Removed.)
             // (A variant that privatised the two coarse levels' gradient rows in shared memory -- shared-memory atomics, one flush
             // per CTA -- was measured 2.6x SLOWER at B=8, Lq=10200 (2.51 vs 0.95 ms): the 600 coarse pixels serialise far worse
             // in one SM's shared-memory atomic unit than spread over the L2 slices.  gpurun r2_msda1.log; removed.)
