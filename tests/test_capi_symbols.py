@@ -41,3 +41,17 @@ def test_cpu_tensor_is_rejected_loudly():
     loc = torch.zeros(1, 1, 1, 1, 1, 2); at = torch.zeros(1, 1, 1, 1, 1)
     with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
         ms_deform_attn_forward(v, sh, ls, loc, at, 64)
+
+
+def test_process_wide_settings_round_trip_without_a_gpu():
+    """mdb_set_deterministic / mdb_set_precision are host-side switches: they answer on a machine without a GPU."""
+    import monodetr_b200
+    from monodetr_b200 import tc
+    prev = monodetr_b200.set_deterministic(True)
+    try:
+        assert monodetr_b200.is_deterministic() and _lib.lib().mdb_get_deterministic() == 1
+        assert monodetr_b200.set_deterministic(False) is True and not monodetr_b200.is_deterministic()
+    finally:
+        monodetr_b200.set_deterministic(prev)
+    mode = tc.get_precision()
+    assert mode in ("bf16x3", "tf32x3", "tf32")
