@@ -450,6 +450,9 @@ def msda_fused(value, spatial_shapes, level_start_index, off, logits, ref):
 
 # ---- one encoder layer as ONE autograd node ---------------------------------------------------------------------------
 ENC_FUSED = not os.environ.get("MDB_NO_ENC_FUSED")
+# the six weight-gradient GEMMs of a layer's backward on the side stream, beside the data-gradient chain (LayerNorm / dropout / MSDA
+# scatter / dgrad GEMMs) they do not feed
+ENC_WGRAD_SIDE = bool(os.environ.get("MDB_ENC_WGRAD_SIDE"))
 
 
 class _EncoderLayer(Function):
@@ -503,29 +506,43 @@ class _EncoderLayer(Function):
         M = B * S
         if hd is None:
             hd = h
+        fork = _Fork() if ENC_WGRAD_SIDE else None
+
+        def wgrad(dy, x):
+            """Weight + bias gradient; with the side stream: launched there once everything the main stream has produced so far
+            (dy, x among it) is complete.  dy / x stay referenced by this frame until the join below, so the caching allocator cannot
+            hand their memory to later main-stream work while the side stream still reads it."""
+            if fork is None:
+                return tc.linear_wgrad(dy, x, with_bias_grad=True)
+            fork.side.wait_stream(fork.main)
+            with torch.cuda.stream(fork.side):
+                return tc.linear_wgrad(dy, x, with_bias_grad=True)
+
         # ---- LayerNorm 2, FFN ------------------------------------------------------------------------------------------------
         d_src1_res, d_f, dg2, dbe2 = K.add_layernorm_backward(dout.reshape(M, C), src1, f, g2, mean2, rstd2, drop, site + 2, seed)
-        dW2, db2 = tc.linear_wgrad(d_f, hd, with_bias_grad=True)
+        dW2, db2 = wgrad(d_f, hd)
         d_h = tc.linear_dgrad(d_f, s2, relu_mask=h)                        # ReLU mask in the epilogue (commutes with the dropout scaling)
         if drop > 0:
             d_h = dropout_raw(d_h, drop, site + 1, seed)
-        dW1, db1 = tc.linear_wgrad(d_h, src1, with_bias_grad=True)
+        dW1, db1 = wgrad(d_h, src1)
         d_src1 = tc.linear_dgrad(d_h, s1, residual=d_src1_res)             # + the residual branch of LayerNorm 2
         # ---- LayerNorm 1, output projection, deformable attention ----------------------------------------------------------
         d_x_res, d_a, dg1, dbe1 = K.add_layernorm_backward(d_src1, x2, a, g1, mean1, rstd1, drop, site, seed)
-        dWu, dbu = tc.linear_wgrad(d_a, o2, with_bias_grad=True)
+        dWu, dbu = wgrad(d_a, o2)
         d_o = tc.linear_dgrad(d_a, su)
         gv, goff, glog = msda_fused_backward_raw(value.view(B, S, n_heads, C // n_heads), shapes, lsi, off.view(B, S, -1),
                                                  logits.view(B, S, -1), refc, d_o.view(B, S, C))
         gv2, goff2, glog2 = gv.view(M, C), goff.view(M, -1), glog.view(M, -1)
-        dWo, dbo = tc.linear_wgrad(goff2, q2, with_bias_grad=True)
-        dWa, dba = tc.linear_wgrad(glog2, q2, with_bias_grad=True)
-        dWv, dbv = tc.linear_wgrad(gv2, x2, with_bias_grad=True)
+        dWo, dbo = wgrad(goff2, q2)
+        dWa, dba = wgrad(glog2, q2)
+        dWv, dbv = wgrad(gv2, x2)
         d_q = tc.linear_dgrad(goff2, so)
         d_q = tc.linear_dgrad(glog2, sa, residual=d_q)                     # d query = both projections' data gradients
         d_pos = d_q.view(B, S, C).sum_to_size(pos_shape) if ctx.needs_input_grad[1] else None
         d_src = tc.linear_dgrad(gv2, sv, residual=d_x_res)                 # + the residual branch of LayerNorm 1
         d_src.add_(d_q)                                                     # + the query path (query = src + pos)
+        if fork is not None:
+            fork.join(dWv, dbv, dWo, dbo, dWa, dba, dWu, dbu, dW1, db1, dW2, db2)
         return (d_src.view(B, S, C), d_pos, None, None, None, None, None, None, None, None, None,
                 dWv, dbv, dWo, dbo, dWa, dba, dWu, dbu, dg1, dbe1, dW1, db1, dW2, db2, dg2, dbe2)
 
