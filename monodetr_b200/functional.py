@@ -507,7 +507,7 @@ class _EncoderLayer(Function):
         M = B * S
         if hd is None:
             hd = h
-        fork = _Fork() if ENC_WGRAD_SIDE else None
+        fork = _Fork() if (ENC_WGRAD_SIDE and dout.is_cuda) else None
 
         def wgrad(dy, x):
             """Weight + bias gradient; with the side stream: launched there once everything the main stream has produced so far
