@@ -524,6 +524,40 @@ class FakeLib:
         return 0
 
 
+    # ---- the steps either side of the path -----------------------------------------------------------------------
+    def mdb_adamw_step_f32(self, p, g, m, v, n, n_decay, beta1, omb1, beta2, omb2, eps, wd, step_size, step_size_dev, stream):
+        """lib/helpers/optimizer_helper.py:104-127 per element; weight decay on the first n_decay elements of the flat layout."""
+        P, G, M, V = f32(p, n), f32(g, n), f32(m, n), f32(v, n)
+        step = float(f32(step_size_dev, 1)[0]) if step_size_dev else step_size
+        M.mul_(beta1).add_(G, alpha=omb1)
+        V.mul_(beta2).addcmul_(G, G, value=omb2)
+        decay = torch.zeros(n)
+        decay[:n_decay] = wd
+        P.add_((P * decay).addcdiv_(M, V.sqrt().add_(eps), value=1), alpha=-step)
+        return 0
+
+    def mdb_extract_dets_f32(self, logits, boxes, dim3, depth, angle, B, Q, C, topk, dets, stream):
+        from oracle import decode as od
+        f32(dets, B, topk, 37).copy_(torch.from_numpy(od.extract_dets(
+            f32(logits, B, Q, C).numpy(), f32(boxes, B, Q, 6).numpy(), f32(dim3, B, Q, 3).numpy(), f32(depth, B, Q, 2).numpy(),
+            f32(angle, B, Q, 24).numpy(), topk)))
+        return 0
+
+    def mdb_decode_dets_f32(self, dets, img_size, P2, mean, B, topk, C, threshold, out, count, stream):
+        from oracle import decode as od
+        d = f32(dets, B, topk, 37)
+        rows = od.decode_dets(d.numpy(), f32(img_size, B, 2).numpy(), f32(P2, B, 3, 4).numpy(), f32(mean, C, 3).numpy(), threshold)
+        o = f32(out, B, topk, 14)
+        o.zero_()
+        cnt = _buf(count, B, ctypes.c_int32, torch.int32)
+        for b in range(B):
+            # (the kernel keeps the PREFIX of the score-sorted rows that reach the threshold; with sorted scores that is every such row)
+            cnt[b] = len(rows[b])
+            if rows[b]:
+                o[b, :len(rows[b])] = torch.tensor(rows[b], dtype=torch.float64).float()
+        return 0
+
+
 class _Stream:
     cuda_stream = 0
 
