@@ -32,17 +32,19 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "tf32x3"])
-def test_train_mode_forward_and_every_gradient_match_the_oracle(monkeypatch, precision):
+@pytest.mark.parametrize("precision,batch,deterministic", [("bf16x3", 1, False), ("tf32x3", 1, False), ("bf16x3", 2, True)])
+def test_train_mode_forward_and_every_gradient_match_the_oracle(monkeypatch, precision, batch, deterministic):
     """bf16x3 = the default configuration: weights split once per forward (tc.prepacked / SplitW), the one-node encoder layer with
-    its weight gradients forked onto the side stream; tf32x3: fp32 packed weights, the encoder layer as separate nodes."""
+    its weight gradients forked onto the side stream; tf32x3: fp32 packed weights, the encoder layer as separate nodes; the
+    reproducible mode (mdb_set_deterministic) sends every MSDeformAttn call down the two-step (pre-processing + op) path."""
     from monodetr_b200.bench_model import surrogate_loss
     fake, m, sd = _build(monkeypatch, precision)
+    fake.deterministic = int(deterministic)
     from monodetr_b200 import functional as Fn
     node_calls, node = [], Fn.encoder_layer
     monkeypatch.setattr(Fn, "encoder_layer", lambda *a, **k: (node_calls.append(1), node(*a, **k))[1])
     m.train()
-    images, calibs, sizes = om.synthetic_inputs(1, 0, H=96, W=320)
+    images, calibs, sizes = om.synthetic_inputs(batch, 0, H=96, W=320)
     out = m(images, calibs, None, sizes)
     surrogate_loss(out).backward()
 
@@ -83,12 +85,14 @@ def test_train_mode_forward_and_every_gradient_match_the_oracle(monkeypatch, pre
     assert errs[len(errs) // 2][0] < med_bar, errs[len(errs) // 2]
     for err, name, scale in errs:
         assert err < worst_bar or scale < 1e-6, (name, err, scale)
-    assert len(node_calls) == (3 if precision == "bf16x3" else 0)      # the three encoder layers ran as one autograd node each
+    assert len(node_calls) == (3 if precision == "bf16x3" and not deterministic else 0)      # the three encoder layers as one autograd node each
+    if deterministic:
+        assert fake.calls.get("mdb_msda_fused_forward_f32", 0) == 0 and fake.calls["mdb_msda_prep_forward_f32"] == 6
     # the wiring went through the library boundary, not around it
     conv = ("mdb_conv2d_forward_bf16x3", "mdb_conv2d_dgrad_bf16x3", "mdb_pack_gemm_weights_bf16x3") if precision == "bf16x3" else \
         ("mdb_conv2d_forward_f32", "mdb_conv2d_dgrad_f32", "mdb_pack_conv_weights_multi_f32")
     for fn in conv + ("mdb_conv2d_wgrad_bias_f32", "mdb_attention_forward_f32",
-               "mdb_attention_backward_f32", "mdb_msda_fused_forward_f32", "mdb_msda_fused_backward_f32", "mdb_msda_prep_forward_f32",
+               "mdb_attention_backward_f32", "mdb_msda_prep_forward_f32",) + (() if deterministic else ("mdb_msda_fused_forward_f32", "mdb_msda_fused_backward_f32")) + (
                "mdb_add_layernorm_backward_f32", "mdb_groupnorm_backward_f32", "mdb_head_depth_backward_f32",
                "mdb_depth_tail_backward_f32", "mdb_box_refine_backward_f32", "mdb_stem_conv7x7_bn_relu_f32"):
         assert fake.calls.get(fn, 0) > 0, fn
